@@ -1,0 +1,763 @@
+/*
+ * ssl_oracle.c -- CPU oracle (TEST INFRASTRUCTURE ONLY, see ssl_oracle.h).
+ *
+ * PARITY UNPINNED (no Bullet, no reference golden vectors).
+ * Plain C restatement of the step the reference performs through
+ *   world_step -> world_step_delta -> btDiscreteDynamicsWorld::stepSimulation
+ *   (reference src/sslsim.cpp:307-326)
+ * for the scene it builds (reference src/sslsim.cpp:16-28, 44-49, 63-100,
+ * 136-203, 238-252), following docs/STEP_SPEC.md.  Bullet semantics are those
+ * of Bullet 2.82 (btSequentialImpulseConstraintSolver::setupContactConstraint,
+ * solveGroupCacheFriendlyIterations; btDiscreteDynamicsWorld::
+ * internalSingleStepSimulation), restated from their published algorithm.
+ *
+ * Build: gcc -O2 -ffp-contract=off (no fast-math).  All arithmetic is IEEE
+ * binary32 with the association order written here; the CUDA kernel is
+ * compiled with --fmad=false and follows the same order, so the two agree
+ * bit-for-bit in practice (tests still state a tolerance).
+ */
+#include "ssl_oracle.h"
+#include <math.h>
+#include <pthread.h>
+#include <string.h>
+
+/* ---- scene constants (reference src/sslsim.cpp) ------------------------- */
+#define BALL_R 0.0215f        /* :17 BALL_DIAM/2 */
+#define BALL_M 0.046f         /* :18 */
+#define ROBOT_R 0.09f         /* :19 ROBOT_DIAM/2 */
+#define ROBOT_M 2.0f          /* :21 */
+#define DROP_Z 0.5f           /* :22 */
+#define WHEEL_R 0.025f        /* :23 WHEEL_DIAM/2: robot origin rests at this height */
+#define ROBOT_ZLO (-0.02f)    /* :89-90 chassis centre +0.0525, half height 0.0725 */
+#define ROBOT_ZHI 0.125f
+#define WHEEL_RC 0.085f       /* :115 wheel contact radius ROBOT_DIAM/2 - WHEEL_WIDTH/2 */
+#define GRAV 9.80665f         /* :240 */
+#define CEIL_Z 10.0f          /* :187 */
+#define E_BALL_PLANE 0.5f     /* :47 x :141 (product rule) */
+#define E_ROBOT_PLANE 0.2f    /* :87 x :141 */
+#define E_BALL_ROBOT 0.1f     /* :47 x :87 */
+#define E_ROBOT_ROBOT 0.04f   /* :87 x :87 */
+#define E_GOAL 0.0f           /* goal bodies keep Bullet's default restitution 0 */
+#define MU 0.25f              /* Bullet default friction 0.5 x 0.5 */
+/* Bullet 2.82 defaults */
+#define MARGIN 0.02f          /* gContactBreakingThreshold */
+#define ERP 0.2f
+#define ERP2 0.8f
+#define SPLIT_THRESH (-0.04f)
+#define REST_THRESH 0.2f      /* restitution velocity threshold (Bullet >= 2.87 default) */
+#define FLT_EPS 1.1920929e-07f
+#define TWO_PI 6.2831855f
+/* wheel mounting angles: reference :27-28 rotates by WHEELS_ANGLE about (0,0,-1) */
+static const float WSIN[4] = {-0.8660254f, -0.70710677f, 0.70710677f, 0.8660254f};
+static const float WCOS[4] = {0.5f, -0.70710677f, -0.70710677f, 0.5f};
+
+#define MAX_SERIAL_ROWS 64
+
+void orc_params_default(orc_params *p) {
+  memset(p, 0, sizeof *p);
+  p->flags = 0;
+  p->solver_iterations = 10;
+  p->kick_reach = 0.015f;
+  p->kick_halfwidth = 0.04f;
+  p->kick_max_height = 0.03f;
+  p->wheel_kp = 24.0f;
+  p->wheel_fmax = 4.0f;
+  p->robot_yaw_inertia = 0.0081f; /* 1/2 m r^2 */
+  p->dribble_kd = 60.0f;
+  p->dribble_cd = 8.0f;
+  p->dribble_amax = 12.0f;
+  p->dribble_reach = 0.03f;
+  p->mu_roll = 0.03f;
+}
+
+/* ---- counter RNG --------------------------------------------------------- */
+static uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+float orc_u01(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t h = mix64(seed);
+  h = mix64(h ^ a);
+  h = mix64(h ^ b);
+  h = mix64(h ^ c);
+  return (float)(uint32_t)(h >> 40) * 5.9604645e-08f; /* 2^-24 */
+}
+
+/* ---- sin/cos (STEP_SPEC 3.1): Cody-Waite by pi/2, cephes polynomials ------ */
+void orc_sincos(float x, float *s, float *c) {
+  float kf = rintf(x * 0.63661975f);
+  int k = (int)kf;
+  float r = x - kf * 1.5703125f;
+  r = r - kf * 4.837512969970703125e-4f;
+  r = r - kf * 7.54978995489188216e-8f;
+  float z = r * r;
+  float sp = -1.9515295891e-4f * z + 8.3321608736e-3f;
+  sp = sp * z - 1.6666654611e-1f;
+  sp = sp * z * r + r;
+  float cp = 2.443315711809948e-5f * z - 1.388731625493765e-3f;
+  cp = cp * z + 4.166664568298827e-2f;
+  cp = cp * z * z - 0.5f * z + 1.0f;
+  switch (k & 3) {
+  case 0: *s = sp; *c = cp; break;
+  case 1: *s = cp; *c = -sp; break;
+  case 2: *s = -sp; *c = -cp; break;
+  default: *s = -cp; *c = sp; break;
+  }
+}
+
+/* ---- derived field geometry (reference src/sslsim.cpp:145-203, field.h:36-42) */
+typedef struct {
+  float half_len, half_wid, limit_x, limit_y;
+  float goal_half_w, goal_back, goal_height;
+  float lo[6][3], hi[6][3];
+} field_derived;
+
+static void derive_field(const orc_field *f, field_derived *d) {
+  d->half_len = f->field_length / 2;
+  d->half_wid = f->field_width / 2;
+  d->limit_x = f->field_length / 2 + f->boundary_width + f->referee_width;
+  d->limit_y = f->field_width / 2 + f->boundary_width + f->referee_width;
+  d->goal_half_w = f->goal_width / 2;
+  d->goal_back = d->half_len + f->goal_depth;
+  d->goal_height = f->goal_height;
+  float ww = f->goal_wall_width, gd = f->goal_depth, gw = f->goal_width, gh = f->goal_height;
+  /* -x goal at (-L/2,0,0), identity (reference :198-199) */
+  float sx = -d->half_len + (-gd / 2 - ww / 2), shx = gd / 2 + ww / 2;
+  float sy = gw / 2 + ww / 2, shy = ww / 2;
+  float rx = -d->half_len + (-gd - ww / 2), rhx = ww / 2, rhy = gw / 2;
+  float cz = gh / 2, hz = gh / 2;
+  /* 0: side wall at -y, 1: side wall at +y, 2: rear wall */
+  d->lo[0][0] = sx - shx; d->hi[0][0] = sx + shx; d->lo[0][1] = -sy - shy; d->hi[0][1] = -sy + shy;
+  d->lo[1][0] = sx - shx; d->hi[1][0] = sx + shx; d->lo[1][1] = sy - shy;  d->hi[1][1] = sy + shy;
+  d->lo[2][0] = rx - rhx; d->hi[2][0] = rx + rhx; d->lo[2][1] = -rhy;      d->hi[2][1] = rhy;
+  for (int k = 0; k < 3; k++) { d->lo[k][2] = cz - hz; d->hi[k][2] = cz + hz; }
+  /* +x goal: same compound rotated 180 deg about z at (+L/2,0,0) (reference :200-201) */
+  for (int k = 0; k < 3; k++) {
+    d->lo[3 + k][0] = -d->hi[k][0]; d->hi[3 + k][0] = -d->lo[k][0];
+    d->lo[3 + k][1] = -d->hi[k][1]; d->hi[3 + k][1] = -d->lo[k][1];
+    d->lo[3 + k][2] = d->lo[k][2];  d->hi[3 + k][2] = d->hi[k][2];
+  }
+}
+
+/* ---- contact rows -------------------------------------------------------- */
+typedef struct {
+  float nx, ny, nz, target;
+  float tx, ty, tz, push_target;
+  int a, b;   /* body indices; b = -1 for a static partner; normal points b -> a */
+  float mu;   /* 0 disables the friction row */
+  int spin;   /* ball-ground row in spin mode: friction row carries the angular term */
+  float acc_n, acc_f, acc_p;
+} row_t;
+
+static float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* btPlaneSpace1: first tangent of the plane orthogonal to n */
+static void plane_space1(float nx, float ny, float nz, float *tx, float *ty, float *tz) {
+  if (fabsf(nz) > 0.70710677f) {
+    float a = ny * ny + nz * nz;
+    float k = 1.0f / sqrtf(a);
+    *tx = 0.0f; *ty = -nz * k; *tz = ny * k;
+  } else {
+    float a = nx * nx + ny * ny;
+    float k = 1.0f / sqrtf(a);
+    *tx = -ny * k; *ty = nx * k; *tz = 0.0f;
+  }
+}
+
+typedef struct {
+  int n, R;
+  float inv_h, h;
+  const orc_vec4 *pos, *vel; /* substep-start state (vel after kick) */
+  const float *hvx, *hvy, *hvz; /* vel + external impulses */
+  int spin_mode;
+  float ball_margin;
+  const uint32_t *cflags;    /* per robot command flags or NULL */
+} gen_ctx;
+
+/* finish a row given (n, dist, a, b, e, mu): Bullet 2.82 setupContactConstraint */
+static void finish_row(const gen_ctx *g, row_t *r, float nx, float ny, float nz, float dist,
+                       int a, int b, float e, float mu) {
+  r->nx = nx; r->ny = ny; r->nz = nz; r->a = a; r->b = b; r->mu = mu; r->spin = 0;
+  r->acc_n = r->acc_f = r->acc_p = 0.0f;
+  float rvx = g->vel[a].x, rvy = g->vel[a].y, rvz = g->vel[a].z;
+  if (b >= 0) { rvx = rvx - g->vel[b].x; rvy = rvy - g->vel[b].y; rvz = rvz - g->vel[b].z; }
+  float vn = nx * rvx + ny * rvy + nz * rvz;
+  float rest = (-vn > REST_THRESH) ? e * (-vn) : 0.0f;
+  float push = 0.0f;
+  if (dist > 0.0f) {
+    /* speculative row: the gap may close but not overshoot; if it closes within
+     * this substep and the pair is restitutive, reflect now (STEP_SPEC 4.3) */
+    float hx = g->hvx[a], hy = g->hvy[a], hz = g->hvz[a];
+    if (b >= 0) { hx = hx - g->hvx[b]; hy = hy - g->hvy[b]; hz = hz - g->hvz[b]; }
+    float hn = nx * hx + ny * hy + nz * hz;
+    int closing = (hn * g->h + dist) < 0.0f;
+    r->target = (closing && rest > 0.0f) ? rest : -(dist * g->inv_h);
+  } else if (dist > SPLIT_THRESH) {
+    r->target = rest + -(dist * ERP) * g->inv_h;
+  } else {
+    r->target = rest;
+    push = -(dist * ERP2) * g->inv_h;
+  }
+  r->push_target = push;
+  /* single friction direction along the lateral relative velocity */
+  float lx = rvx - nx * vn, ly = rvy - ny * vn, lz = rvz - nz * vn;
+  float l2 = lx * lx + ly * ly + lz * lz;
+  if (l2 > FLT_EPS) {
+    float k = 1.0f / sqrtf(l2);
+    r->tx = lx * k; r->ty = ly * k; r->tz = lz * k;
+  } else {
+    plane_space1(nx, ny, nz, &r->tx, &r->ty, &r->tz);
+  }
+}
+
+static int is_ball(const gen_ctx *g, int b) { return b == g->R; }
+
+/* ground row of body b (always evaluated; one row stands for the robot's four
+ * wheel contacts: identical linear Jacobians, zero inverse inertia about x,y) */
+static int gen_ground(const gen_ctx *g, int b, row_t *r) {
+  int ball = is_ball(g, b);
+  float dist = g->pos[b].z - (ball ? BALL_R : WHEEL_R);
+  float margin = ball ? g->ball_margin : MARGIN;
+  if (!(dist <= margin)) return 0;
+  float mu = MU;
+  if (!ball && g->cflags && (g->cflags[b] & ORC_CMD_DRIVE)) mu = 0.0f; /* wheels replace sliding friction */
+  finish_row(g, r, 0.0f, 0.0f, 1.0f, dist, b, -1, ball ? E_BALL_PLANE : E_ROBOT_PLANE, mu);
+  if (ball && g->spin_mode) {
+    /* friction direction from the contact-point velocity (v + w x r_c), r_c = (0,0,-r) */
+    float cvx = g->vel[b].x - BALL_R * g->vel[b].w; /* vel.w = omega_y */
+    float cvy = g->vel[b].y + BALL_R * g->pos[b].w; /* pos.w = omega_x */
+    float l2 = cvx * cvx + cvy * cvy;
+    if (l2 > FLT_EPS) {
+      float k = 1.0f / sqrtf(l2);
+      r->tx = cvx * k; r->ty = cvy * k; r->tz = 0.0f;
+    } else {
+      plane_space1(0.0f, 0.0f, 1.0f, &r->tx, &r->ty, &r->tz);
+    }
+    r->spin = 1;
+  }
+  return 1;
+}
+
+/* static rows other than the ground for body b, canonical order:
+ * ceiling, wall -x, wall +x, wall -y, wall +y, goal boxes 0..5 */
+static int gen_statics(const gen_ctx *g, const field_derived *d, int b, row_t *out, int cap) {
+  int cnt = 0;
+  int ball = is_ball(g, b);
+  float px = g->pos[b].x, py = g->pos[b].y, pz = g->pos[b].z;
+  float rad = ball ? BALL_R : ROBOT_R;
+  float margin = ball ? g->ball_margin : MARGIN;
+  float e = ball ? E_BALL_PLANE : E_ROBOT_PLANE;
+  float dist;
+#define EMIT(NX, NY, NZ, DIST, E)                                                     \
+  do {                                                                                \
+    if (cnt < cap) finish_row(g, &out[cnt], (NX), (NY), (NZ), (DIST), b, -1, (E), MU); \
+    cnt++;                                                                            \
+  } while (0)
+  dist = CEIL_Z - (pz + (ball ? BALL_R : ROBOT_ZHI));
+  if (dist <= margin) EMIT(0.0f, 0.0f, -1.0f, dist, e);
+  dist = (px + d->limit_x) - rad;
+  if (dist <= margin) EMIT(1.0f, 0.0f, 0.0f, dist, e);
+  dist = (d->limit_x - px) - rad;
+  if (dist <= margin) EMIT(-1.0f, 0.0f, 0.0f, dist, e);
+  dist = (py + d->limit_y) - rad;
+  if (dist <= margin) EMIT(0.0f, 1.0f, 0.0f, dist, e);
+  dist = (d->limit_y - py) - rad;
+  if (dist <= margin) EMIT(0.0f, -1.0f, 0.0f, dist, e);
+  for (int k = 0; k < 6; k++) {
+    const float *lo = d->lo[k], *hi = d->hi[k];
+    float nx, ny, nz;
+    if (ball) {
+      float cx = clampf(px, lo[0], hi[0]), cy = clampf(py, lo[1], hi[1]), cz = clampf(pz, lo[2], hi[2]);
+      float dx = px - cx, dy = py - cy, dz = pz - cz;
+      float d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 > 0.0f) {
+        float dd = sqrtf(d2);
+        nx = dx / dd; ny = dy / dd; nz = dz / dd;
+        dist = dd - BALL_R;
+      } else { /* centre inside the box: minimum-penetration face, order -x +x -y +y -z +z */
+        float pen = px - lo[0]; nx = -1.0f; ny = 0.0f; nz = 0.0f;
+        float q = hi[0] - px; if (q < pen) { pen = q; nx = 1.0f; ny = 0.0f; nz = 0.0f; }
+        q = py - lo[1]; if (q < pen) { pen = q; nx = 0.0f; ny = -1.0f; nz = 0.0f; }
+        q = hi[1] - py; if (q < pen) { pen = q; nx = 0.0f; ny = 1.0f; nz = 0.0f; }
+        q = pz - lo[2]; if (q < pen) { pen = q; nx = 0.0f; ny = 0.0f; nz = -1.0f; }
+        q = hi[2] - pz; if (q < pen) { pen = q; nx = 0.0f; ny = 0.0f; nz = 1.0f; }
+        dist = -pen - BALL_R;
+      }
+    } else {
+      float cx = clampf(px, lo[0], hi[0]), cy = clampf(py, lo[1], hi[1]);
+      float dx = px - cx, dy = py - cy;
+      float d2 = dx * dx + dy * dy;
+      float hx, hy, sh;
+      if (d2 > 0.0f) {
+        float dd = sqrtf(d2);
+        hx = dx / dd; hy = dy / dd;
+        sh = dd - ROBOT_R;
+      } else {
+        float pen = px - lo[0]; hx = -1.0f; hy = 0.0f;
+        float q = hi[0] - px; if (q < pen) { pen = q; hx = 1.0f; hy = 0.0f; }
+        q = py - lo[1]; if (q < pen) { pen = q; hx = 0.0f; hy = -1.0f; }
+        q = hi[1] - py; if (q < pen) { pen = q; hx = 0.0f; hy = 1.0f; }
+        sh = -pen - ROBOT_R;
+      }
+      float s_up = (pz + ROBOT_ZLO) - hi[2]; /* robot above the box */
+      float s_dn = lo[2] - (pz + ROBOT_ZHI); /* robot below the box */
+      float sv = s_up >= s_dn ? s_up : s_dn;
+      if (sh >= sv) { nx = hx; ny = hy; nz = 0.0f; dist = sh; }
+      else { nx = 0.0f; ny = 0.0f; nz = s_up >= s_dn ? 1.0f : -1.0f; dist = sv; }
+    }
+    if (dist <= margin) EMIT(nx, ny, nz, dist, E_GOAL);
+  }
+#undef EMIT
+  return cnt;
+}
+
+/* robot i vs robot j (i < j): parallel capped cylinders; normal points j -> i */
+static int gen_robot_robot(const gen_ctx *g, int i, int j, row_t *r) {
+  float dx = g->pos[i].x - g->pos[j].x, dy = g->pos[i].y - g->pos[j].y;
+  float d2 = dx * dx + dy * dy;
+  float lim = 2.0f * ROBOT_R + MARGIN;
+  if (!(d2 <= lim * lim)) return 0;
+  float dd = sqrtf(d2);
+  float hx = 1.0f, hy = 0.0f;
+  if (d2 > 1e-12f) { hx = dx / dd; hy = dy / dd; }
+  float sh = dd - 2.0f * ROBOT_R;
+  float zi = g->pos[i].z, zj = g->pos[j].z;
+  float s_up = (zi + ROBOT_ZLO) - (zj + ROBOT_ZHI); /* i above j */
+  float s_dn = (zj + ROBOT_ZLO) - (zi + ROBOT_ZHI);
+  float sv = s_up >= s_dn ? s_up : s_dn;
+  float nx, ny, nz, dist;
+  if (sh >= sv) { nx = hx; ny = hy; nz = 0.0f; dist = sh; }
+  else { nx = 0.0f; ny = 0.0f; nz = s_up >= s_dn ? 1.0f : -1.0f; dist = sv; }
+  if (!(dist <= MARGIN)) return 0;
+  finish_row(g, r, nx, ny, nz, dist, i, j, E_ROBOT_ROBOT, MU);
+  return 1;
+}
+
+/* ball vs robot i: sphere vs capped cylinder, exact closest feature; normal robot -> ball */
+static int gen_ball_robot(const gen_ctx *g, int i, row_t *r) {
+  int B = g->R;
+  float dx = g->pos[B].x - g->pos[i].x, dy = g->pos[B].y - g->pos[i].y;
+  float d2 = dx * dx + dy * dy;
+  float lim = ROBOT_R + BALL_R + g->ball_margin;
+  if (!(d2 <= lim * lim)) return 0;
+  float dd = sqrtf(d2);
+  float hx = 1.0f, hy = 0.0f;
+  if (d2 > 1e-12f) { hx = dx / dd; hy = dy / dd; }
+  float sh = dd - ROBOT_R;
+  float qz = g->pos[B].z - g->pos[i].z;
+  float s_lo = ROBOT_ZLO - qz, s_hi = qz - ROBOT_ZHI;
+  float sv = s_hi >= s_lo ? s_hi : s_lo;
+  float sg = s_hi >= s_lo ? 1.0f : -1.0f;
+  float nx, ny, nz, dist;
+  if (sh > 0.0f && sv > 0.0f) {
+    float ee = sqrtf(sh * sh + sv * sv);
+    float kh = sh / ee, kv = sv / ee;
+    nx = hx * kh; ny = hy * kh; nz = sg * kv;
+    dist = ee - BALL_R;
+  } else if (sh >= sv) { nx = hx; ny = hy; nz = 0.0f; dist = sh - BALL_R; }
+  else { nx = 0.0f; ny = 0.0f; nz = sg; dist = sv - BALL_R; }
+  if (!(dist <= g->ball_margin)) return 0;
+  finish_row(g, r, nx, ny, nz, dist, B, i, E_BALL_ROBOT, MU);
+  return 1;
+}
+
+/* ---- one substep (Bullet internalSingleStepSimulation, STEP_SPEC 4) ------- */
+static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4 *pos,
+                    orc_vec4 *vel, uint32_t *aux, const orc_cmd *cmd, float h) {
+  const int N = R + 1, B = R;
+  const float inv_h = 1.0f / h;
+  const int spin_mode = (p->flags & ORC_F_BALL_SPIN) != 0;
+  float ex[ORC_MAX_BODIES], ey[ORC_MAX_BODIES], ez[ORC_MAX_BODIES], ew[ORC_MAX_BODIES];
+  uint32_t cflags[ORC_MAX_BODIES];
+  for (int b = 0; b < N; b++) { ex[b] = ey[b] = ez[b] = ew[b] = 0.0f; cflags[b] = 0; }
+
+  /* 4.1 actuation (new functionality; command schema reference protos/grSim_Commands.proto) */
+  if (cmd) {
+    int kicker = -1, dribbler = -1;
+    float kvx = 0, kvy = 0, kvz = 0, dax = 0, day = 0;
+    const float bx = pos[B].x, by = pos[B].y, bz = pos[B].z;
+    const float bvx = vel[B].x, bvy = vel[B].y;
+    for (int r = 0; r < R; r++) {
+      const orc_cmd *c = &cmd[r];
+      cflags[r] = c->flags;
+      float s, co;
+      orc_sincos(pos[r].w, &s, &co);
+      float dx = bx - pos[r].x, dy = by - pos[r].y;
+      float fwd = co * dx + s * dy;
+      float lat = co * dy - s * dx;
+      int grounded = (pos[r].z - WHEEL_R) <= 0.005f;
+      int low = (bz - BALL_R) <= p->kick_max_height;
+      int in_lat = fabsf(lat) <= p->kick_halfwidth;
+      if (grounded && low && in_lat && fwd > 0.0f) {
+        if (c->kickspeedx > 0.0f && fwd <= ROBOT_R + BALL_R + p->kick_reach) {
+          kicker = r; /* highest index wins */
+          kvx = vel[r].x + co * c->kickspeedx;
+          kvy = vel[r].y + s * c->kickspeedx;
+          kvz = c->kickspeedz;
+        }
+        if ((c->flags & ORC_CMD_SPINNER) && fwd <= ROBOT_R + BALL_R + p->dribble_reach) {
+          dribbler = r;
+          float tx = pos[r].x + (ROBOT_R + BALL_R) * co, ty = pos[r].y + (ROBOT_R + BALL_R) * s;
+          float ax = p->dribble_kd * (tx - bx) + p->dribble_cd * (vel[r].x - bvx);
+          float ay = p->dribble_kd * (ty - by) + p->dribble_cd * (vel[r].y - bvy);
+          float a2 = ax * ax + ay * ay;
+          if (a2 > p->dribble_amax * p->dribble_amax) {
+            float k = p->dribble_amax / sqrtf(a2);
+            ax = ax * k; ay = ay * k;
+          }
+          dax = ax; day = ay;
+        }
+      }
+      if ((c->flags & ORC_CMD_DRIVE) && grounded) {
+        float u[4];
+        if (c->flags & ORC_CMD_WHEELS) {
+          for (int i = 0; i < 4; i++) u[i] = c->wheel[i] * WHEEL_R;
+        } else {
+          for (int i = 0; i < 4; i++)
+            u[i] = (WCOS[i] * c->wheel[1] - WSIN[i] * c->wheel[0]) + WHEEL_RC * c->wheel[2];
+        }
+        float vf = co * vel[r].x + s * vel[r].y;
+        float vl = co * vel[r].y - s * vel[r].x;
+        float ff = 0.0f, fl = 0.0f, tq = 0.0f;
+        for (int i = 0; i < 4; i++) {
+          float act = (WCOS[i] * vl - WSIN[i] * vf) + WHEEL_RC * vel[r].w;
+          float fi = clampf(p->wheel_kp * (u[i] - act), -p->wheel_fmax, p->wheel_fmax);
+          ff = ff - WSIN[i] * fi;
+          fl = fl + WCOS[i] * fi;
+          tq = tq + fi;
+        }
+        float k = h / ROBOT_M;
+        ex[r] = (co * ff - s * fl) * k;
+        ey[r] = (s * ff + co * fl) * k;
+        ew[r] = (WHEEL_RC * tq) * (h / p->robot_yaw_inertia);
+      }
+    }
+    if (kicker >= 0) {
+      vel[B].x = kvx; vel[B].y = kvy; vel[B].z = kvz;
+      float s2 = kvx * kvx + kvy * kvy + kvz * kvz;
+      memcpy(&aux[ORC_AUX_PEAK2], &s2, 4);
+      aux[ORC_AUX_STATUS] = (aux[ORC_AUX_STATUS] & ~0xFFu) | (uint32_t)kicker | (1u << 15);
+      aux[ORC_AUX_OUTS] += 1u << 16;
+    }
+    if (dribbler >= 0 && kicker < 0) { ex[B] = dax * h; ey[B] = day * h; }
+  }
+  /* 4.2 gravity as an external impulse (Bullet: totalForce * invMass * h) */
+  const float gh = GRAV * h;
+  for (int b = 0; b < N; b++) ez[b] = ez[b] - gh;
+
+  /* solver velocities start at v + external impulse */
+  float vx[ORC_MAX_BODIES], vy[ORC_MAX_BODIES], vz[ORC_MAX_BODIES];
+  float qx[ORC_MAX_BODIES], qy[ORC_MAX_BODIES], qz[ORC_MAX_BODIES]; /* push velocity */
+  float invm[ORC_MAX_BODIES];
+  for (int b = 0; b < N; b++) {
+    vx[b] = vel[b].x + ex[b]; vy[b] = vel[b].y + ey[b]; vz[b] = vel[b].z + ez[b];
+    qx[b] = qy[b] = qz[b] = 0.0f;
+    invm[b] = b == B ? 1.0f / BALL_M : 1.0f / ROBOT_M;
+  }
+
+  /* 4.3 contact generation on substep-start positions */
+  gen_ctx g;
+  g.n = N; g.R = R; g.h = h; g.inv_h = inv_h; g.pos = pos; g.vel = vel; g.spin_mode = spin_mode;
+  g.cflags = cmd ? cflags : 0;
+  g.hvx = vx; g.hvy = vy; g.hvz = vz;
+  {
+    float s2 = vx[B] * vx[B] + vy[B] * vy[B] + vz[B] * vz[B];
+    g.ball_margin = MARGIN + h * sqrtf(s2); /* stands in for Bullet's predictive (CCD) contact */
+  }
+  row_t rows[MAX_SERIAL_ROWS];
+  row_t ground[ORC_MAX_BODIES];
+  int has_ground[ORC_MAX_BODIES];
+  const int cap = N <= 16 ? 32 : MAX_SERIAL_ROWS;
+  int nrows = 0, overflow = 0;
+  for (int i = 0; i < R; i++)
+    for (int j = i + 1; j < R; j++) {
+      row_t r;
+      if (gen_robot_robot(&g, i, j, &r)) { if (nrows < cap) rows[nrows++] = r; else overflow = 1; }
+    }
+  for (int i = 0; i < R; i++) {
+    row_t r;
+    if (gen_ball_robot(&g, i, &r)) { if (nrows < cap) rows[nrows++] = r; else overflow = 1; }
+  }
+  for (int b = 0; b < N; b++) {
+    row_t tmp[11];
+    int c = gen_statics(&g, d, b, tmp, 11);
+    for (int k = 0; k < c; k++) { if (nrows < cap) rows[nrows++] = tmp[k]; else overflow = 1; }
+  }
+  int nground = 0;
+  for (int b = 0; b < N; b++) { has_ground[b] = gen_ground(&g, b, &ground[b]); nground += has_ground[b]; }
+  if (overflow) aux[ORC_AUX_STATUS] |= 1u << 16;
+  aux[ORC_AUX_CONTACTS] += (uint32_t)(nrows + nground);
+
+  /* 4.4 split-impulse pass (Bullet solveGroupCacheFriendlySplitImpulseIterations) */
+  int deep = 0;
+  for (int k = 0; k < nrows; k++) deep |= rows[k].push_target > 0.0f;
+  for (int b = 0; b < N; b++) deep |= has_ground[b] && ground[b].push_target > 0.0f;
+  if (deep) {
+    for (int it = 0; it < p->solver_iterations; it++) {
+      for (int k = 0; k < nrows + N; k++) {
+        row_t *r;
+        if (k < nrows) r = &rows[k];
+        else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
+        if (!(r->push_target > 0.0f)) continue;
+        int a = r->a, b = r->b;
+        float ima = invm[a], imb = b >= 0 ? invm[b] : 0.0f;
+        float meff = 1.0f / (ima + imb);
+        float rx = qx[a], ry = qy[a], rz = qz[a];
+        if (b >= 0) { rx = rx - qx[b]; ry = ry - qy[b]; rz = rz - qz[b]; }
+        float vn = r->nx * rx + r->ny * ry + r->nz * rz;
+        float dl = (r->push_target - vn) * meff;
+        float sum = r->acc_p + dl;
+        if (sum < 0.0f) { dl = -r->acc_p; sum = 0.0f; }
+        r->acc_p = sum;
+        float ka = dl * ima;
+        qx[a] = qx[a] + r->nx * ka; qy[a] = qy[a] + r->ny * ka; qz[a] = qz[a] + r->nz * ka;
+        if (b >= 0) {
+          float kb = dl * imb;
+          qx[b] = qx[b] - r->nx * kb; qy[b] = qy[b] - r->ny * kb; qz[b] = qz[b] - r->nz * kb;
+        }
+      }
+    }
+  }
+
+  /* 4.5 velocity iterations: all normal rows, then all friction rows (Bullet
+   * solveSingleIteration without SOLVER_INTERLEAVE_CONTACT_AND_FRICTION) */
+  float wx = pos[B].w, wy = vel[B].w; /* ball spin (omega_x, omega_y) */
+  const float ball_invm = 1.0f / BALL_M;
+  const float spin_meff = 1.0f / (ball_invm + 2.5f * ball_invm);
+  const float spin_gain = (2.5f * ball_invm) / BALL_R; /* r / I */
+  for (int it = 0; it < p->solver_iterations; it++) {
+    for (int k = 0; k < nrows + N; k++) {
+      row_t *r;
+      if (k < nrows) r = &rows[k];
+      else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
+      int a = r->a, b = r->b;
+      float ima = invm[a], imb = b >= 0 ? invm[b] : 0.0f;
+      float meff = 1.0f / (ima + imb);
+      float rx = vx[a], ry = vy[a], rz = vz[a];
+      if (b >= 0) { rx = rx - vx[b]; ry = ry - vy[b]; rz = rz - vz[b]; }
+      float vn = r->nx * rx + r->ny * ry + r->nz * rz;
+      float dl = (r->target - vn) * meff;
+      float sum = r->acc_n + dl;
+      if (sum < 0.0f) { dl = -r->acc_n; sum = 0.0f; }
+      r->acc_n = sum;
+      float ka = dl * ima;
+      vx[a] = vx[a] + r->nx * ka; vy[a] = vy[a] + r->ny * ka; vz[a] = vz[a] + r->nz * ka;
+      if (b >= 0) {
+        float kb = dl * imb;
+        vx[b] = vx[b] - r->nx * kb; vy[b] = vy[b] - r->ny * kb; vz[b] = vz[b] - r->nz * kb;
+      }
+    }
+    for (int k = 0; k < nrows + N; k++) {
+      row_t *r;
+      if (k < nrows) r = &rows[k];
+      else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
+      if (!(r->mu > 0.0f) || !(r->acc_n > 0.0f)) continue; /* Bullet: friction only if totalImpulse > 0 */
+      int a = r->a, b = r->b;
+      float ima = invm[a], imb = b >= 0 ? invm[b] : 0.0f;
+      float rx = vx[a], ry = vy[a], rz = vz[a];
+      if (b >= 0) { rx = rx - vx[b]; ry = ry - vy[b]; rz = rz - vz[b]; }
+      float meff;
+      if (r->spin) {
+        rx = rx - BALL_R * wy;
+        ry = ry + BALL_R * wx;
+        meff = spin_meff;
+      } else {
+        meff = 1.0f / (ima + imb);
+      }
+      float vt = r->tx * rx + r->ty * ry + r->tz * rz;
+      float dl = (0.0f - vt) * meff;
+      float lim = r->mu * r->acc_n;
+      float sum = r->acc_f + dl;
+      if (sum > lim) { dl = lim - r->acc_f; sum = lim; }
+      else if (sum < -lim) { dl = -lim - r->acc_f; sum = -lim; }
+      r->acc_f = sum;
+      float ka = dl * ima;
+      vx[a] = vx[a] + r->tx * ka; vy[a] = vy[a] + r->ty * ka; vz[a] = vz[a] + r->tz * ka;
+      if (b >= 0) {
+        float kb = dl * imb;
+        vx[b] = vx[b] - r->tx * kb; vy[b] = vy[b] - r->ty * kb; vz[b] = vz[b] - r->tz * kb;
+      }
+      if (r->spin) {
+        float kw = dl * spin_gain;
+        wx = wx + r->ty * kw;
+        wy = wy - r->tx * kw;
+      }
+    }
+  }
+
+  /* 4.6 touches, rolling resistance, peak speed */
+  uint32_t touch = 0;
+  int last = -1;
+  for (int k = 0; k < nrows; k++)
+    if (rows[k].a == B && rows[k].b >= 0 && rows[k].acc_n > 0.0f) { touch |= 1u << rows[k].b; last = rows[k].b; }
+  if (last >= 0) aux[ORC_AUX_STATUS] = (aux[ORC_AUX_STATUS] & ~0xFFu) | (uint32_t)last;
+  aux[ORC_AUX_TOUCH] |= touch;
+  if (spin_mode && has_ground[B] && ground[B].acc_n > 0.0f) {
+    float s2 = vx[B] * vx[B] + vy[B] * vy[B];
+    if (s2 > 0.0f) {
+      float sp = sqrtf(s2);
+      float dec = (p->mu_roll * GRAV) * h;
+      float k = sp > dec ? (sp - dec) / sp : 0.0f;
+      vx[B] = vx[B] * k; vy[B] = vy[B] * k; wx = wx * k; wy = wy * k;
+    }
+  }
+  {
+    float s2 = vx[B] * vx[B] + vy[B] * vy[B] + vz[B] * vz[B];
+    float pk; memcpy(&pk, &aux[ORC_AUX_PEAK2], 4);
+    if (s2 > pk) memcpy(&aux[ORC_AUX_PEAK2], &s2, 4);
+  }
+
+  /* 4.7 write back and integrate (semi-implicit Euler; split-impulse push first) */
+  for (int b = 0; b < N; b++) {
+    vel[b].x = vx[b]; vel[b].y = vy[b]; vel[b].z = vz[b];
+    if (deep) {
+      pos[b].x = pos[b].x + qx[b] * h; pos[b].y = pos[b].y + qy[b] * h; pos[b].z = pos[b].z + qz[b] * h;
+    }
+    pos[b].x = pos[b].x + vx[b] * h; pos[b].y = pos[b].y + vy[b] * h; pos[b].z = pos[b].z + vz[b] * h;
+    if (b != B) {
+      float wz = vel[b].w + ew[b];
+      vel[b].w = wz;
+      float yaw = pos[b].w + wz * h;
+      if (yaw >= TWO_PI) yaw = yaw - TWO_PI;
+      else if (yaw <= -TWO_PI) yaw = yaw + TWO_PI;
+      pos[b].w = yaw;
+    }
+  }
+  pos[B].w = wx; vel[B].w = wy;
+}
+
+/* ---- step = substeps + events (STEP_SPEC 5) -------------------------------- */
+static void step_events(const field_derived *d, int R, const orc_vec4 *pos, uint32_t *aux) {
+  const int B = R;
+  float x = pos[B].x, y = pos[B].y, z = pos[B].z;
+  int mouth = fabsf(y) < d->goal_half_w && z < d->goal_height;
+  int in_pos = mouth && x > d->half_len && x < d->goal_back;
+  int in_neg = mouth && x < -d->half_len && x > -d->goal_back;
+  int out = (fabsf(x) > d->half_len || fabsf(y) > d->half_wid) && !in_pos && !in_neg;
+  uint32_t st = aux[ORC_AUX_STATUS];
+  int p_pos = (st >> 8) & 1, p_neg = (st >> 9) & 1, p_out = (st >> 10) & 1;
+  uint32_t ev = 0;
+  if (in_pos && !p_pos) { ev |= 1u << 12; aux[ORC_AUX_GOALS] += 1u; }        /* blue attacks +x */
+  if (in_neg && !p_neg) { ev |= 1u << 13; aux[ORC_AUX_GOALS] += 1u << 16; }  /* yellow attacks -x */
+  if (out && !p_out) { ev |= 1u << 14; aux[ORC_AUX_OUTS] += 1u; }
+  st = (st & ~(7u << 8)) | ((uint32_t)in_pos << 8) | ((uint32_t)in_neg << 9) | ((uint32_t)out << 10);
+  st = (st & ~(7u << 12)) | ev; /* bit15 (kicked) was set during the substeps and is kept */
+  int bad = 0;
+  for (int b = 0; b <= R; b++)
+    bad |= !(pos[b].x - pos[b].x == 0.0f) || !(pos[b].y - pos[b].y == 0.0f) || !(pos[b].z - pos[b].z == 0.0f);
+  if (bad) st |= 1u << 17;
+  aux[ORC_AUX_STATUS] = st;
+  aux[ORC_AUX_TOUCHES] += (uint32_t)__builtin_popcount(aux[ORC_AUX_TOUCH]);
+}
+
+void orc_step(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *pos, orc_vec4 *vel,
+              uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h) {
+  field_derived d;
+  derive_field(f, &d);
+  for (int s = 0; s < n_steps; s++) {
+    aux[ORC_AUX_TOUCH] = 0;
+    aux[ORC_AUX_STATUS] &= ~(1u << 15);
+    for (int k = 0; k < substeps; k++) substep(&d, p, n_robots, pos, vel, aux, cmd, h);
+    step_events(&d, n_robots, pos, aux);
+  }
+}
+
+/* ---- init / commands / gather ---------------------------------------------- */
+void orc_init_world(const orc_field *f, int R, uint64_t seed, uint64_t world_id, int mode,
+                    orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux) {
+  const int B = R;
+  for (int b = 0; b <= R; b++) { vel[b].x = vel[b].y = vel[b].z = vel[b].w = 0.0f; }
+  for (int k = 0; k < 8; k++) aux[k] = 0;
+  aux[ORC_AUX_STATUS] = 0xFFu;
+  if (mode == 0) {
+    /* reference src/sslsim.cpp:34-42 ranges, :446 drop height; ball :251 */
+    float w = f->field_length / 2 - ROBOT_R, hgt = f->field_width / 2 - ROBOT_R;
+    for (int r = 0; r < R; r++) {
+      float u0 = orc_u01(seed, world_id, (uint64_t)r, 0), u1 = orc_u01(seed, world_id, (uint64_t)r, 1),
+            u2 = orc_u01(seed, world_id, (uint64_t)r, 2);
+      pos[r].x = -w + u0 * (2.0f * w);
+      pos[r].y = -hgt + u1 * (2.0f * hgt);
+      pos[r].z = DROP_Z;
+      pos[r].w = u2 * TWO_PI;
+    }
+    pos[B].x = 0.0f; pos[B].y = 0.0f; pos[B].z = DROP_Z; pos[B].w = 0.0f;
+  } else {
+    /* crowded +x penalty area, resting */
+    float x0 = f->field_length / 2 - 1.8f, xw = 1.7f, yw = 1.8f;
+    for (int b = 0; b <= R; b++) {
+      float x = 0, y = 0;
+      for (int t = 0; t < 64; t++) {
+        x = x0 + orc_u01(seed, world_id, (uint64_t)b, (uint64_t)(4 * t + 8)) * xw;
+        y = -yw + orc_u01(seed, world_id, (uint64_t)b, (uint64_t)(4 * t + 9)) * (2.0f * yw);
+        int ok = 1;
+        for (int c = 0; c < b; c++) {
+          float dx = x - pos[c].x, dy = y - pos[c].y;
+          if (dx * dx + dy * dy < 0.19f * 0.19f) ok = 0;
+        }
+        if (ok) break;
+      }
+      pos[b].x = x; pos[b].y = y;
+      pos[b].z = b == B ? BALL_R : WHEEL_R;
+      pos[b].w = b == B ? 0.0f : orc_u01(seed, world_id, (uint64_t)b, 2) * TWO_PI;
+    }
+  }
+}
+
+void orc_gen_commands(int R, uint64_t seed, uint64_t world_id, uint64_t period, int kind, orc_cmd *cmd) {
+  for (int r = 0; r < R; r++) {
+    uint64_t key = period * 64u + (uint64_t)r;
+    for (int i = 0; i < 4; i++) cmd[r].wheel[i] = -40.0f + orc_u01(seed, world_id, key, 100u + (uint64_t)i) * 80.0f;
+    cmd[r].flags = ORC_CMD_DRIVE | ORC_CMD_WHEELS;
+    cmd[r].kickspeedx = 0.0f; cmd[r].kickspeedz = 0.0f; cmd[r].pad = 0;
+    if (kind == 1) {
+      cmd[r].flags |= ORC_CMD_SPINNER;
+      cmd[r].kickspeedx = orc_u01(seed, world_id, key, 104u) * 6.5f;
+      cmd[r].kickspeedz = (r & 1) ? orc_u01(seed, world_id, key, 105u) * 3.0f : 0.0f;
+    }
+  }
+}
+
+int orc_gather(int R, const orc_vec4 *pos, const int *ids, float *out) {
+  int n = 0;
+  const orc_vec4 *b = &pos[R];
+  out[n++] = 1.0f; out[n++] = b->x; out[n++] = b->y; out[n++] = b->z; out[n++] = b->x; out[n++] = b->y;
+  for (int r = 0; r < R; r++) {
+    float yaw = pos[r].w == 0.0f ? -0.0f : pos[r].w; /* reference src/sslsim.cpp:441-442 quirk */
+    out[n++] = 1.0f; out[n++] = (float)ids[r];
+    out[n++] = pos[r].x; out[n++] = pos[r].y; out[n++] = yaw; out[n++] = pos[r].x; out[n++] = pos[r].y;
+  }
+  return n;
+}
+
+/* ---- many worlds, optional threads (timing baseline) ------------------------ */
+typedef struct {
+  const orc_field *f; const orc_params *p; int R, w0, w1;
+  orc_vec4 *pos, *vel; uint32_t *aux; const orc_cmd *cmd; int n_steps, substeps; float h;
+} job_t;
+
+static void *job_run(void *arg) {
+  job_t *j = (job_t *)arg;
+  int N = j->R + 1;
+  for (int w = j->w0; w < j->w1; w++)
+    orc_step(j->f, j->p, j->R, j->pos + (size_t)w * N, j->vel + (size_t)w * N, j->aux + (size_t)w * 8,
+             j->cmd ? j->cmd + (size_t)w * j->R : 0, j->n_steps, j->substeps, j->h);
+  return 0;
+}
+
+void orc_step_many(const orc_field *f, const orc_params *p, int R, int W, orc_vec4 *pos, orc_vec4 *vel,
+                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, int threads) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  job_t jobs[256];
+  pthread_t th[256];
+  for (int t = 0; t < threads; t++) {
+    job_t j = {f, p, R, (int)((long long)W * t / threads), (int)((long long)W * (t + 1) / threads),
+               pos, vel, aux, cmd, n_steps, substeps, h};
+    jobs[t] = j;
+  }
+  if (threads == 1) { job_run(&jobs[0]); return; }
+  for (int t = 0; t < threads; t++) pthread_create(&th[t], 0, job_run, &jobs[t]);
+  for (int t = 0; t < threads; t++) pthread_join(th[t], 0);
+}

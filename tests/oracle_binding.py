@@ -1,0 +1,122 @@
+"""ctypes binding of the CPU oracle (oracle/libssl_oracle.so).
+
+Test infrastructure only: imported by tests/, bench.py's cpu_baseline / --impl reference
+leg and __graft_entry__.smoke().  Never imported by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = None
+
+FIELD_2014_SINGLE = (0.010, 6.050, 4.050, 0.250, 0.425, 0.700, 0.180, 0.020, 0.500, 0.800, 0.350, 0.200, 0.750, 0.400, 0.165)
+FIELD_2014_DOUBLE = (0.010, 8.090, 6.050, 0.250, 0.425, 1.000, 0.180, 0.020, 0.500, 1.000, 0.500, 0.200, 1.000, 0.400, 0.165)
+FIELD_2015 = (0.010, 9.000, 6.000, 0.250, 0.450, 1.000, 0.180, 0.020, 0.500, 1.000, 0.500, 0.200, 1.000, 0.400, 0.165)
+FIELD_DIV_A = (0.010, 12.0, 9.0, 0.30, 0.40, 1.8, 0.18, 0.02, 0.5, 1.0, 0.5, 0.2, 1.0, 0.4, 0.16)
+
+H = np.float32(1.0 / 60 / 2)  # reference src/sslsim.cpp:309
+
+
+class Field(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "line_width", "field_length", "field_width", "boundary_width", "referee_width", "goal_width",
+        "goal_depth", "goal_wall_width", "center_circle_radius", "defense_radius", "defense_stretch",
+        "free_kick_from_defense_dist", "penalty_spot_from_field_line_dist", "penalty_line_from_spot_dist",
+        "goal_height")]
+
+
+class Params(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("solver_iterations", C.c_int32),
+                ("kick_reach", C.c_float), ("kick_halfwidth", C.c_float), ("kick_max_height", C.c_float),
+                ("wheel_kp", C.c_float), ("wheel_fmax", C.c_float), ("robot_yaw_inertia", C.c_float),
+                ("dribble_kd", C.c_float), ("dribble_cd", C.c_float), ("dribble_amax", C.c_float),
+                ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("reserved", C.c_float * 3)]
+
+
+CMD_DTYPE = np.dtype([("wheel", np.float32, 4), ("kickspeedx", np.float32), ("kickspeedz", np.float32),
+                      ("flags", np.uint32), ("pad", np.uint32)])
+CMD_DRIVE, CMD_WHEELS, CMD_SPINNER = 1, 2, 4
+F_BALL_SPIN = 1
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ORACLE_DIR, "libssl_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        fp = C.c_void_p
+        L.orc_params_default.argtypes = [C.POINTER(Params)]
+        L.orc_step.argtypes = [C.POINTER(Field), C.POINTER(Params), C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, C.c_float]
+        L.orc_init_world.argtypes = [C.POINTER(Field), C.c_int, C.c_uint64, C.c_uint64, C.c_int, fp, fp, fp]
+        L.orc_gen_commands.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, fp]
+        L.orc_gather.argtypes = [C.c_int, fp, fp, fp]
+        L.orc_gather.restype = C.c_int
+        L.orc_u01.argtypes = [C.c_uint64] * 4
+        L.orc_u01.restype = C.c_float
+        L.orc_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_step_many.argtypes = [C.POINTER(Field), C.POINTER(Params), C.c_int, C.c_int, fp, fp, fp, fp,
+                                    C.c_int, C.c_int, C.c_float, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def field(vals=FIELD_2015):
+    return Field(*vals)
+
+
+def default_params(**kw):
+    p = Params()
+    lib().orc_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Worlds:
+    """W independent oracle worlds, world-major arrays pos/vel [W, R+1, 4], aux [W, 8], cmd [W, R]."""
+
+    def __init__(self, n_worlds, n_robots, fld=FIELD_2015, params=None, seed=0x5351, mode=0, world0=0):
+        self.W, self.R = n_worlds, n_robots
+        self.field = field(fld)
+        self.params = params if params is not None else default_params()
+        self.pos = np.zeros((n_worlds, n_robots + 1, 4), np.float32)
+        self.vel = np.zeros_like(self.pos)
+        self.aux = np.zeros((n_worlds, 8), np.uint32)
+        self.cmd = None
+        self.seed, self.world0 = seed, world0
+        L = lib()
+        for w in range(n_worlds):
+            L.orc_init_world(C.byref(self.field), n_robots, seed, world0 + w, mode,
+                             _ptr(self.pos[w]), _ptr(self.vel[w]), _ptr(self.aux[w]))
+
+    def gen_commands(self, period, kind=0):
+        if self.cmd is None:
+            self.cmd = np.zeros((self.W, self.R), CMD_DTYPE)
+        L = lib()
+        for w in range(self.W):
+            L.orc_gen_commands(self.R, self.seed, self.world0 + w, period, kind, _ptr(self.cmd[w]))
+
+    def step(self, n_steps=1, substeps=2, h=H, threads=1):
+        lib().orc_step_many(C.byref(self.field), C.byref(self.params), self.R, self.W, _ptr(self.pos),
+                            _ptr(self.vel), _ptr(self.aux), _ptr(self.cmd), n_steps, substeps,
+                            C.c_float(float(h)), threads)
+
+    def gather(self, w, ids):
+        out = np.zeros(6 + 7 * self.R, np.float32)
+        ids = np.asarray(ids, np.int32)
+        n = lib().orc_gather(self.R, _ptr(self.pos[w]), _ptr(ids), _ptr(out))
+        return out[:n]
