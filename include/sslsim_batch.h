@@ -1,0 +1,189 @@
+/*
+ * sslsim_batch.h -- batched extension of the ssl-sim C API: thousands of
+ * independent SSL worlds stepped in lockstep by hand-written sm_100a kernels.
+ *
+ * Additive to sslsim.h (no reference symbol changes).  Plain C ABI: pointers,
+ * sizes and PODs only.  Each entry point names the reference interface it
+ * stands in for (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - One CUDA stream per batch.  world_batch_step / set_commands / replace_*
+ *    are asynchronous on it; read/gather/reduce calls synchronise.
+ *    Calls on one batch are not thread-safe; different batches are independent.
+ *  - New calls return int status: 0 ok, <0 SSLSIM_E_*; CUDA errors are sticky
+ *    per batch (world_batch_last_error / world_batch_error_string).
+ *  - World-major host layouts: state[w][body][4] floats with the ball as the
+ *    last body, aux[w][8] words, commands[w][robot].
+ *  - There is no CPU fallback: without a CUDA device new_world_batch fails.
+ */
+#ifndef SSLSIM_B200_BATCH_H
+#define SSLSIM_B200_BATCH_H
+#include <stddef.h>
+#include <stdint.h>
+#include "sslsim.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct WorldBatch;
+
+#define SSLSIM_MAX_ROBOTS 31 /* one lane per body: 31 robots + ball per warp */
+
+enum {
+  SSLSIM_OK = 0,
+  SSLSIM_E_ARG = -1,    /* bad argument */
+  SSLSIM_E_CUDA = -2,   /* CUDA runtime error (sticky) */
+  SSLSIM_E_NOMEM = -3,
+  SSLSIM_E_SPACE = -4   /* output buffer too small */
+};
+
+/* Builder-defined tunables of the parts of the step that have no upstream
+ * implementation (docs/STEP_SPEC.md section 2).  64 bytes. */
+struct SslSimParams {
+  uint32_t flags;            /* SSLSIM_F_* */
+  int32_t solver_iterations; /* Bullet default 10 (btContactSolverInfo) */
+  float kick_reach, kick_halfwidth, kick_max_height;
+  float wheel_kp, wheel_fmax, robot_yaw_inertia;
+  float dribble_kd, dribble_cd, dribble_amax, dribble_reach;
+  float mu_roll;
+  float reserved[3];
+};
+#define SSLSIM_F_BALL_SPIN 1u /* ball rolls (spin state + rolling resistance) instead of the reference's pure sliding */
+void sslsim_params_default(struct SslSimParams *p);
+
+/* Per-robot command, 32 bytes.  Schema: protos/grSim_Commands.proto:1-14
+ * (kickspeedx, kickspeedz, veltangent, velnormal, velangular, spinner,
+ * wheelsspeed, wheel1..4); wheel order and mounting: src/sslsim.cpp:26-28,115-122. */
+struct RobotCommand {
+  float wheel[4]; /* SSLSIM_CMD_WHEELS: wheel1..4 [rad/s]; else {veltangent, velnormal, velangular, unused} */
+  float kickspeedx, kickspeedz;
+  uint32_t flags; /* SSLSIM_CMD_* */
+  uint32_t pad;
+};
+#define SSLSIM_CMD_DRIVE 1u   /* wheel-driven; 0 = passive rigid body (the reference's behaviour, sslsim.cpp:361) */
+#define SSLSIM_CMD_WHEELS 2u  /* grSim 'wheelsspeed' */
+#define SSLSIM_CMD_SPINNER 4u /* grSim 'spinner' */
+
+/* Replacement records.  Schema: protos/grSim_Replacement.proto:1-19; effect on
+ * the pose as robot_set_pos / ball_set_vec (src/sslsim.cpp:445-450, 384-388):
+ * the body is re-dropped from 0.5 m.  Robot velocity is untouched (as
+ * upstream); the ball takes (vx, vy, 0). */
+struct RobotReplacement { int32_t world; int32_t robot; float x, y, dir; };
+struct BallReplacement { int32_t world; float x, y, vx, vy; };
+
+/* aux words per world (8 x u32) */
+enum {
+  SSLSIM_AUX_STATUS = 0,  /* [7:0] last touching robot index (0xFF none); bit8/9/10 ball currently in +x goal /
+                             -x goal / out; bits 12..15 events of the last step: goal for blue (+x goal),
+                             goal for yellow (-x goal), ball out, kicked; bit16 contact-row overflow (sticky);
+                             bit17 non-finite state (sticky) */
+  SSLSIM_AUX_PEAK2 = 1,   /* f32 bits: peak |v_ball|^2 since the last kick */
+  SSLSIM_AUX_TOUCH = 2,   /* robots that touched the ball during the last step (bit i = robot i) */
+  SSLSIM_AUX_RSVD = 3,
+  SSLSIM_AUX_GOALS = 4,   /* goals_blue | goals_yellow << 16 */
+  SSLSIM_AUX_OUTS = 5,    /* ball-out count | kicks << 16 */
+  SSLSIM_AUX_TOUCHES = 6, /* sum over steps of popcount(touch mask) */
+  SSLSIM_AUX_CONTACTS = 7 /* active contact rows summed over all substeps */
+};
+
+/* Episode statistics of one batch (K4), also the NCCL all-gather payload. */
+struct BatchStats {
+  uint64_t goals_blue, goals_yellow, ball_out, kicks, touches, contacts;
+  uint64_t bad_worlds;   /* worlds with the non-finite or overflow flag */
+  uint64_t checksum;     /* order-independent sum over worlds of a hash of (world id, state bits) */
+};
+
+/* ---- lifecycle: stands in for new_world / world_add_robot x 2R / delete_world
+ * (src/world.h:21-23,41; src/sslsim.cpp:238-252,358-365) for n_worlds at once.
+ * Roster order is B0,Y0,B1,Y1,... as src/main.c:65-68.  Initial poses come from
+ * a counter RNG keyed (seed, first_world_id + w, body) over the ranges of
+ * random_robot_pos2 (src/sslsim.cpp:34-42), so shards of a larger batch are
+ * reproducible on any GPU. */
+struct WorldBatch *new_world_batch(const struct FieldGeometry *field, int n_worlds,
+                                   int robots_per_team, int device, uint64_t seed);
+/* init_mode 0: reference-style uniform placement dropped from 0.5 m;
+ * 1: all bodies resting inside the +x penalty area (crowded).
+ * params NULL = defaults.  n_robots is the total per world (any split; roster
+ * alternates blue/yellow). */
+struct WorldBatch *new_world_batch_ex(const struct FieldGeometry *field, int n_worlds,
+                                      int n_robots, int device, uint64_t seed,
+                                      uint64_t first_world_id, int init_mode,
+                                      const struct SslSimParams *params);
+void delete_world_batch(struct WorldBatch *batch);
+int world_batch_reset(struct WorldBatch *batch, uint64_t seed, int init_mode); /* re-run the init kernel */
+
+int world_batch_world_count(const struct WorldBatch *batch);
+int world_batch_robot_count(const struct WorldBatch *batch); /* robots per world */
+int world_batch_device(const struct WorldBatch *batch);
+unsigned int world_batch_frame_number(const struct WorldBatch *batch); /* src/sslsim.cpp:325 */
+double world_batch_timestamp(const struct WorldBatch *batch);          /* src/sslsim.cpp:324 (fp32 accumulator) */
+
+/* ---- the step: world_step / world_step_delta (src/world.h:25-27,
+ * src/sslsim.cpp:307-326) for every world, n_steps times in one launch with
+ * the current commands held fixed.  world_batch_step = n_steps x (2 substeps
+ * of 1/120 s). */
+int world_batch_step(struct WorldBatch *batch, int n_steps);
+int world_batch_step_delta(struct WorldBatch *batch, int n_steps, int substeps, float fixed_time_step);
+int world_batch_sync(struct WorldBatch *batch);
+
+/* ---- command input (no upstream implementation; schema grSim_Commands.proto).
+ * host/device array of n_worlds * n_robots records, world-major.  NULL (or
+ * world_batch_clear_commands) = every robot passive, i.e. reference mode. */
+int world_batch_set_commands(struct WorldBatch *batch, const struct RobotCommand *host_cmds);
+int world_batch_set_commands_device(struct WorldBatch *batch, const struct RobotCommand *dev_cmds);
+int world_batch_clear_commands(struct WorldBatch *batch);
+/* synthetic command stream generated on the device: kind 0 = wheel
+ * speeds U[-40,40] rad/s, kind 1 = kind 0 + spinner + kicks; keyed
+ * (seed, world id, robot, period). */
+int world_batch_gen_commands(struct WorldBatch *batch, uint64_t period, int kind);
+
+/* ---- replacement input: robot_set_pos / ball_set_vec (src/robot.h:23,
+ * src/ball.h:19) as a sparse device scatter (K2). */
+int world_batch_replace_robots(struct WorldBatch *batch, const struct RobotReplacement *recs, int n);
+int world_batch_replace_balls(struct WorldBatch *batch, const struct BallReplacement *recs, int n);
+
+/* ---- state readout / injection (bulk form of the getters/setters of
+ * src/robot.h:22-26, src/ball.h:18-26).  Any pointer may be NULL. */
+int world_batch_read_state(struct WorldBatch *batch, float *pos, float *vel, uint32_t *aux);
+int world_batch_write_state(struct WorldBatch *batch, const float *pos, const float *vel, const uint32_t *aux);
+int world_batch_read_aux(struct WorldBatch *batch, uint32_t *aux);
+/* zero-copy: device pointers of the live buffers (pos/vel: float4 [W][R+1];
+ * aux: u32 [W][8]; cmd: RobotCommand [W][R] or NULL) */
+int world_batch_device_state(struct WorldBatch *batch, void **pos, void **vel, void **aux, void **cmd);
+
+/* ---- detection gather (K3): the per-object loops of serialize_world
+ * (src/serialize.cpp:25-65) for n observed worlds.  Record per world, floats:
+ * ball {confidence, x, y, z, pixel_x, pixel_y} then per robot in world order
+ * {confidence, robot_id, x, y, orientation, pixel_x, pixel_y}; 6 + 7*R floats.
+ * Returns the number of bytes written or <0. */
+int world_batch_gather_detections(struct WorldBatch *batch, const int *world_ids, int n,
+                                  void *out, size_t capacity);
+size_t world_batch_detection_record_size(const struct WorldBatch *batch);
+
+/* ---- legacy view: member i of the batch as a `struct World *` usable with
+ * every sslsim.h call (host-mirrored; getters synchronise).  Owned by the batch. */
+struct World *world_batch_get_world(struct WorldBatch *batch, int index);
+
+/* ---- episode statistics (K4): per-batch reduction on the device. */
+int world_batch_reduce_stats(struct WorldBatch *batch, struct BatchStats *out);
+
+/* ---- stream / timing helpers (CUDA events on the batch's own stream) */
+void *world_batch_stream(struct WorldBatch *batch);             /* cudaStream_t */
+int world_batch_set_stream(struct WorldBatch *batch, void *cuda_stream); /* run on a caller-owned stream */
+int world_batch_timer_start(struct WorldBatch *batch);
+int world_batch_timer_stop(struct WorldBatch *batch, float *elapsed_ms); /* synchronises */
+/* kernel-only time: enable, then read the sum over step_worlds launches since
+ * the last reset (events bracketing each launch); reading synchronises */
+int world_batch_enable_kernel_timing(struct WorldBatch *batch, int on);
+int world_batch_kernel_time(struct WorldBatch *batch, float *total_ms, int *launches, int reset);
+/* tuning: lanes per world (16 or 32; 0 = automatic) */
+int world_batch_set_lanes_per_world(struct WorldBatch *batch, int lanes);
+
+int world_batch_last_error(const struct WorldBatch *batch);
+const char *world_batch_error_string(const struct WorldBatch *batch);
+const char *sslsim_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,390 @@
+"""sslsim_b200 -- Python host-side mirror of the C ABI in include/sslsim.h and
+include/sslsim_batch.h (libsslsim_b200.so, hand-written sm_100a kernels).
+
+The directory name carries a hyphen (``ssl-sim_b200``), so import it with
+``importlib.import_module("ssl-sim_b200")`` after putting the repo root on
+``sys.path`` (tests/conftest.py, bench.py and __graft_entry__.py do this).
+
+This module is a thin ctypes binding: every compute call goes to the CUDA
+library.  There is no CPU implementation and no fallback: if the shared library
+is missing or no CUDA device is usable, the calls raise.
+Names, argument meaning and error behaviour follow the reference's C API
+(reference src/world.h, src/robot.h, src/ball.h) and its batched extension.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsslsim_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+TEAM_NONE, TEAM_BLUE, TEAM_YELLOW = -1, 0, 1
+CMD_DRIVE, CMD_WHEELS, CMD_SPINNER = 1, 2, 4
+F_BALL_SPIN = 1
+AUX_STATUS, AUX_PEAK2, AUX_TOUCH, AUX_RSVD, AUX_GOALS, AUX_OUTS, AUX_TOUCHES, AUX_CONTACTS = range(8)
+MAX_ROBOTS = 31
+
+CMD_DTYPE = np.dtype([("wheel", np.float32, 4), ("kickspeedx", np.float32), ("kickspeedz", np.float32),
+                      ("flags", np.uint32), ("pad", np.uint32)])
+ROBOT_REPLACEMENT_DTYPE = np.dtype([("world", np.int32), ("robot", np.int32), ("x", np.float32),
+                                    ("y", np.float32), ("dir", np.float32)])
+BALL_REPLACEMENT_DTYPE = np.dtype([("world", np.int32), ("x", np.float32), ("y", np.float32),
+                                   ("vx", np.float32), ("vy", np.float32)])
+
+
+class FieldGeometry(C.Structure):
+    """reference src/field.h:18-34"""
+    _fields_ = [(n, C.c_float) for n in (
+        "line_width", "field_length", "field_width", "boundary_width", "referee_width", "goal_width",
+        "goal_depth", "goal_wall_width", "center_circle_radius", "defense_radius", "defense_stretch",
+        "free_kick_from_defense_dist", "penalty_spot_from_field_line_dist", "penalty_line_from_spot_dist",
+        "goal_height")]
+
+    def as_tuple(self):
+        return tuple(getattr(self, n) for n, _ in self._fields_)
+
+
+class SimParams(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("solver_iterations", C.c_int32),
+                ("kick_reach", C.c_float), ("kick_halfwidth", C.c_float), ("kick_max_height", C.c_float),
+                ("wheel_kp", C.c_float), ("wheel_fmax", C.c_float), ("robot_yaw_inertia", C.c_float),
+                ("dribble_kd", C.c_float), ("dribble_cd", C.c_float), ("dribble_amax", C.c_float),
+                ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("reserved", C.c_float * 3)]
+
+
+class Vec2(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+
+class Vec3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class Pos2(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("w", C.c_float)]
+
+
+class Pos3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float),
+                ("wx", C.c_float), ("wy", C.c_float), ("wz", C.c_float)]
+
+
+class BatchStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("goals_blue", "goals_yellow", "ball_out", "kicks", "touches",
+                                          "contacts", "bad_worlds", "checksum")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+# every symbol include/*.h declares: (name, restype, argtypes)
+_VP, _I, _F, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
+LEGACY_SYMBOLS = [
+    ("new_world", _VP, [C.POINTER(FieldGeometry)]), ("clone_world", _VP, [_VP]), ("delete_world", None, [_VP]),
+    ("world_step", None, [_VP]), ("world_step_delta", None, [_VP, _F, _I, _F]),
+    ("world_get_field", C.POINTER(FieldGeometry), [_VP]), ("world_ball_count", _I, [_VP]),
+    ("world_get_ball", _VP, [_VP, _I]), ("world_get_game_ball", _VP, [_VP]),
+    ("world_get_mut_ball", _VP, [_VP, _I]), ("world_get_mut_game_ball", _VP, [_VP]),
+    ("world_robot_count", _I, [_VP]), ("world_get_robot", _VP, [_VP, _I]), ("world_get_mut_robot", _VP, [_VP, _I]),
+    ("world_add_robot", None, [_VP, _I, _I]), ("world_get_frame_number", C.c_uint, [_VP]),
+    ("world_get_timestamp", C.c_double, [_VP]), ("world_bt_dynamics", _VP, [_VP]),
+    ("ball_get_vec", Vec3, [_VP]), ("ball_set_vec", None, [_VP, Vec2]), ("ball_get_pos", Pos3, [_VP]),
+    ("ball_set_pos", None, [_VP, Pos3]), ("ball_get_vel", Pos3, [_VP]), ("ball_set_vel", None, [_VP, Pos3]),
+    ("ball_is_touching_robot", _I, [_VP, _VP]), ("ball_last_touching_robot", _VP, [_VP]),
+    ("ball_get_speed2", _F, [_VP]), ("ball_get_peak_speed2_from_last_kick", _F, [_VP]),
+    ("ball_bt_rigid_body", _VP, [_VP]),
+    ("get_id", _I, [_VP]), ("get_team", _I, [_VP]), ("robot_get_pos", Pos2, [_VP]),
+    ("robot_set_pos", None, [_VP, Pos2]), ("robot_get_vel", Pos2, [_VP]), ("robot_set_vel", None, [_VP, Pos2]),
+    ("robot_is_touching_robot", _I, [_VP, _VP]), ("robot_get_speed2", _F, [_VP]),
+]
+BATCH_SYMBOLS = [
+    ("sslsim_params_default", None, [C.POINTER(SimParams)]),
+    ("new_world_batch", _VP, [C.POINTER(FieldGeometry), _I, _I, _I, _U64]),
+    ("new_world_batch_ex", _VP, [C.POINTER(FieldGeometry), _I, _I, _I, _U64, _U64, _I, C.POINTER(SimParams)]),
+    ("delete_world_batch", None, [_VP]), ("world_batch_reset", _I, [_VP, _U64, _I]),
+    ("world_batch_world_count", _I, [_VP]), ("world_batch_robot_count", _I, [_VP]),
+    ("world_batch_device", _I, [_VP]), ("world_batch_frame_number", C.c_uint, [_VP]),
+    ("world_batch_timestamp", C.c_double, [_VP]),
+    ("world_batch_step", _I, [_VP, _I]), ("world_batch_step_delta", _I, [_VP, _I, _I, _F]),
+    ("world_batch_sync", _I, [_VP]),
+    ("world_batch_set_commands", _I, [_VP, _VP]), ("world_batch_set_commands_device", _I, [_VP, _VP]),
+    ("world_batch_clear_commands", _I, [_VP]), ("world_batch_gen_commands", _I, [_VP, _U64, _I]),
+    ("world_batch_replace_robots", _I, [_VP, _VP, _I]), ("world_batch_replace_balls", _I, [_VP, _VP, _I]),
+    ("world_batch_read_state", _I, [_VP, _VP, _VP, _VP]), ("world_batch_write_state", _I, [_VP, _VP, _VP, _VP]),
+    ("world_batch_read_aux", _I, [_VP, _VP]),
+    ("world_batch_device_state", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    ("world_batch_gather_detections", _I, [_VP, _VP, _I, _VP, C.c_size_t]),
+    ("world_batch_detection_record_size", C.c_size_t, [_VP]),
+    ("world_batch_get_world", _VP, [_VP, _I]),
+    ("world_batch_reduce_stats", _I, [_VP, C.POINTER(BatchStats)]),
+    ("world_batch_stream", _VP, [_VP]), ("world_batch_set_stream", _I, [_VP, _VP]),
+    ("world_batch_timer_start", _I, [_VP]), ("world_batch_timer_stop", _I, [_VP, C.POINTER(_F)]),
+    ("world_batch_enable_kernel_timing", _I, [_VP, _I]),
+    ("world_batch_kernel_time", _I, [_VP, C.POINTER(_F), C.POINTER(_I), _I]),
+    ("world_batch_set_lanes_per_world", _I, [_VP, _I]),
+    ("world_batch_last_error", _I, [_VP]), ("world_batch_error_string", C.c_char_p, [_VP]),
+    ("sslsim_b200_version", C.c_char_p, []),
+]
+DATA_SYMBOLS = ["FIELD_2014_SINGLE", "FIELD_2014_DOUBLE", "FIELD_2015", "FIELD_DIV_A"]
+
+_LIB = None
+
+
+def build(verbose=False):
+    """Compile libsslsim_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s" if not verbose else "-k", "-C", CSRC_DIR], check=True)
+    return LIB_PATH
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("sslsim_b200: %s is missing; build it with __graft_entry__.build() or "
+                               "`make -C ssl-sim_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in LEGACY_SYMBOLS + BATCH_SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def field(name="FIELD_2015"):
+    """One of the library's FieldGeometry constants (reference src/field.c:11-63, + FIELD_DIV_A)."""
+    return FieldGeometry.in_dll(lib(), name)
+
+
+def default_params(**kw):
+    p = SimParams()
+    lib().sslsim_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SslSimError(RuntimeError):
+    pass
+
+
+class WorldBatch:
+    """W independent SSL worlds on one CUDA device (struct WorldBatch)."""
+
+    def __init__(self, n_worlds, n_robots=12, fld="FIELD_2015", device=0, seed=0x5351, first_world_id=0,
+                 init_mode=0, params=None):
+        L = lib()
+        self._field = field(fld) if isinstance(fld, str) else fld
+        self._params = params
+        self._h = L.new_world_batch_ex(C.byref(self._field), n_worlds, n_robots, device, seed, first_world_id,
+                                       init_mode, C.byref(params) if params is not None else None)
+        if not self._h:
+            raise SslSimError("new_world_batch failed (no CUDA device, bad arguments or out of memory); "
+                              "sslsim_b200 has no CPU fallback")
+        self.W, self.R, self.N = n_worlds, n_robots, n_robots + 1
+        self.seed, self.first_world_id = seed, first_world_id
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise SslSimError("sslsim_b200 error %d: %s" % (rc, lib().world_batch_error_string(self._h).decode()))
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().delete_world_batch(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- step ----
+    def step(self, n_steps=1):
+        self._ck(lib().world_batch_step(self._h, n_steps))
+
+    def step_delta(self, n_steps, substeps, h):
+        self._ck(lib().world_batch_step_delta(self._h, n_steps, substeps, C.c_float(float(h))))
+
+    def sync(self):
+        self._ck(lib().world_batch_sync(self._h))
+
+    def reset(self, seed=None, init_mode=0):
+        self._ck(lib().world_batch_reset(self._h, self.seed if seed is None else seed, init_mode))
+
+    # ---- input ----
+    def set_commands(self, cmds):
+        """cmds: array [W, R] of CMD_DTYPE (host) or None for passive robots."""
+        if cmds is None:
+            self._ck(lib().world_batch_clear_commands(self._h))
+            return
+        cmds = np.ascontiguousarray(cmds, dtype=CMD_DTYPE)
+        assert cmds.size == self.W * self.R
+        self._ck(lib().world_batch_set_commands(self._h, _ptr(cmds)))
+
+    def set_commands_ptr(self, host_ptr):
+        self._ck(lib().world_batch_set_commands(self._h, host_ptr))
+
+    def gen_commands(self, period, kind=0):
+        self._ck(lib().world_batch_gen_commands(self._h, period, kind))
+
+    def replace_robots(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=ROBOT_REPLACEMENT_DTYPE)
+        self._ck(lib().world_batch_replace_robots(self._h, _ptr(recs), recs.size))
+
+    def replace_balls(self, recs):
+        recs = np.ascontiguousarray(recs, dtype=BALL_REPLACEMENT_DTYPE)
+        self._ck(lib().world_batch_replace_balls(self._h, _ptr(recs), recs.size))
+
+    # ---- output ----
+    def read_state(self, want_pos=True, want_vel=True, want_aux=True):
+        pos = np.empty((self.W, self.N, 4), np.float32) if want_pos else None
+        vel = np.empty((self.W, self.N, 4), np.float32) if want_vel else None
+        aux = np.empty((self.W, 8), np.uint32) if want_aux else None
+        self._ck(lib().world_batch_read_state(self._h, _ptr(pos), _ptr(vel), _ptr(aux)))
+        return pos, vel, aux
+
+    def read_aux_into(self, host_ptr):
+        self._ck(lib().world_batch_read_aux(self._h, host_ptr))
+
+    def write_state(self, pos=None, vel=None, aux=None):
+        pos = None if pos is None else np.ascontiguousarray(pos, np.float32)
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32)
+        aux = None if aux is None else np.ascontiguousarray(aux, np.uint32)
+        self._ck(lib().world_batch_write_state(self._h, _ptr(pos), _ptr(vel), _ptr(aux)))
+
+    def gather_detections(self, world_ids):
+        ids = np.ascontiguousarray(world_ids, np.int32)
+        out = np.empty((ids.size, 6 + 7 * self.R), np.float32)
+        n = self._ck(lib().world_batch_gather_detections(self._h, _ptr(ids), ids.size, _ptr(out), out.nbytes))
+        assert n == out.nbytes
+        return out
+
+    def reduce_stats(self):
+        st = BatchStats()
+        self._ck(lib().world_batch_reduce_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def device_pointers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        self._ck(lib().world_batch_device_state(self._h, *[C.byref(x) for x in p]))
+        return tuple(x.value for x in p)
+
+    def get_world(self, index):
+        h = lib().world_batch_get_world(self._h, index)
+        if not h:
+            raise IndexError(index)
+        return World(handle=h, owner=self)
+
+    @property
+    def frame_number(self):
+        return lib().world_batch_frame_number(self._h)
+
+    @property
+    def timestamp(self):
+        return lib().world_batch_timestamp(self._h)
+
+    # ---- timing / tuning ----
+    def timer_start(self):
+        self._ck(lib().world_batch_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(lib().world_batch_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def enable_kernel_timing(self, on=True):
+        self._ck(lib().world_batch_enable_kernel_timing(self._h, int(on)))
+
+    def kernel_time(self, reset=True):
+        ms, n = C.c_float(), C.c_int()
+        self._ck(lib().world_batch_kernel_time(self._h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
+
+    def set_lanes_per_world(self, lanes):
+        self._ck(lib().world_batch_set_lanes_per_world(self._h, lanes))
+
+    def set_stream(self, cuda_stream):
+        self._ck(lib().world_batch_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+
+class World:
+    """The reference's single-world API (struct World *), device-backed."""
+
+    def __init__(self, fld="FIELD_2015", handle=None, owner=None):
+        L = lib()
+        self._owner = owner
+        if handle is None:
+            self._field = field(fld) if isinstance(fld, str) else fld
+            handle = L.new_world(C.byref(self._field))
+            if not handle:
+                raise SslSimError("new_world failed (no CUDA device?); sslsim_b200 has no CPU fallback")
+            self._owned = True
+        else:
+            self._owned = False
+        self._h = handle
+
+    def close(self):
+        if self._owned and self._h:
+            lib().delete_world(self._h)
+        self._h = None
+
+    def clone(self):
+        h = lib().clone_world(self._h)
+        if not h:
+            raise SslSimError("clone_world failed")
+        w = World(handle=h)
+        w._owned = True
+        return w
+
+    def step(self):
+        lib().world_step(self._h)
+
+    def step_delta(self, time_step, max_substeps, fixed_time_step):
+        lib().world_step_delta(self._h, time_step, max_substeps, fixed_time_step)
+
+    def add_robot(self, rid, team):
+        lib().world_add_robot(self._h, rid, team)
+
+    @property
+    def robot_count(self):
+        return lib().world_robot_count(self._h)
+
+    @property
+    def ball_count(self):
+        return lib().world_ball_count(self._h)
+
+    @property
+    def frame_number(self):
+        return lib().world_get_frame_number(self._h)
+
+    @property
+    def timestamp(self):
+        return lib().world_get_timestamp(self._h)
+
+    def robot(self, i):
+        return lib().world_get_mut_robot(self._h, i)
+
+    def ball(self):
+        return lib().world_get_mut_game_ball(self._h)
+
+    def robot_pos(self, i):
+        p = lib().robot_get_pos(self.robot(i))
+        return (p.x, p.y, p.w)
+
+    def robot_vel(self, i):
+        p = lib().robot_get_vel(self.robot(i))
+        return (p.x, p.y, p.w)
+
+    def ball_vec(self):
+        v = lib().ball_get_vec(self.ball())
+        return (v.x, v.y, v.z)

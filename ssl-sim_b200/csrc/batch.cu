@@ -1,0 +1,439 @@
+/*
+ * batch.cu -- host side of the batched C ABI (include/sslsim_batch.h): device
+ * buffers, stream, launches.  There is deliberately no CPU implementation of
+ * the step here: every compute entry point launches a kernel or fails.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "batch_internal.h"
+
+/* ---- field constants: values of reference src/field.c:11-63 -------------------- */
+extern "C" {
+const struct FieldGeometry FIELD_2014_SINGLE = {0.010f, 6.050f, 4.050f, 0.250f, 0.425f, 0.700f, 0.180f, 0.020f,
+                                                0.500f, 0.800f, 0.350f, 0.200f, 0.750f, 0.400f, 0.165f};
+const struct FieldGeometry FIELD_2014_DOUBLE = {0.010f, 8.090f, 6.050f, 0.250f, 0.425f, 1.000f, 0.180f, 0.020f,
+                                                0.500f, 1.000f, 0.500f, 0.200f, 1.000f, 0.400f, 0.165f};
+const struct FieldGeometry FIELD_2015 = {0.010f, 9.000f, 6.000f, 0.250f, 0.450f, 1.000f, 0.180f, 0.020f,
+                                         0.500f, 1.000f, 0.500f, 0.200f, 1.000f, 0.400f, 0.165f};
+/* not in the reference: Division-A field, SSL rulebook values */
+const struct FieldGeometry FIELD_DIV_A = {0.010f, 12.0f, 9.0f, 0.30f, 0.40f, 1.8f, 0.18f, 0.02f,
+                                          0.5f, 1.0f, 0.5f, 0.2f, 1.0f, 0.4f, 0.16f};
+}
+
+/* planes and goal boxes of the reference scene (src/sslsim.cpp:145-203, src/field.h:36-42) */
+void sslsim_derive_field(const FieldGeometry *f, DevField *d) {
+  d->half_len = f->field_length / 2;
+  d->half_wid = f->field_width / 2;
+  d->limit_x = f->field_length / 2 + f->boundary_width + f->referee_width;
+  d->limit_y = f->field_width / 2 + f->boundary_width + f->referee_width;
+  d->goal_half_w = f->goal_width / 2;
+  d->goal_back = d->half_len + f->goal_depth;
+  d->goal_height = f->goal_height;
+  d->goal_reach_y = f->goal_width / 2 + f->goal_wall_width;
+  const float ww = f->goal_wall_width, gd = f->goal_depth, gw = f->goal_width, gh = f->goal_height;
+  const float sx = -d->half_len + (-gd / 2 - ww / 2), shx = gd / 2 + ww / 2;
+  const float sy = gw / 2 + ww / 2, shy = ww / 2;
+  const float rx = -d->half_len + (-gd - ww / 2), rhx = ww / 2, rhy = gw / 2;
+  const float cz = gh / 2, hz = gh / 2;
+  d->lo[0][0] = sx - shx; d->hi[0][0] = sx + shx; d->lo[0][1] = -sy - shy; d->hi[0][1] = -sy + shy;
+  d->lo[1][0] = sx - shx; d->hi[1][0] = sx + shx; d->lo[1][1] = sy - shy;  d->hi[1][1] = sy + shy;
+  d->lo[2][0] = rx - rhx; d->hi[2][0] = rx + rhx; d->lo[2][1] = -rhy;      d->hi[2][1] = rhy;
+  for (int k = 0; k < 3; k++) { d->lo[k][2] = cz - hz; d->hi[k][2] = cz + hz; }
+  for (int k = 0; k < 3; k++) {
+    d->lo[3 + k][0] = -d->hi[k][0]; d->hi[3 + k][0] = -d->lo[k][0];
+    d->lo[3 + k][1] = -d->hi[k][1]; d->hi[3 + k][1] = -d->lo[k][1];
+    d->lo[3 + k][2] = d->lo[k][2];  d->hi[3 + k][2] = d->hi[k][2];
+  }
+}
+
+bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return true;
+  if (b) {
+    b->last_error = SSLSIM_E_CUDA;
+    snprintf(b->errstr, sizeof b->errstr, "%s: %s", what, cudaGetErrorString(e));
+  }
+  fprintf(stderr, "sslsim_b200: %s: %s\n", what, cudaGetErrorString(e));
+  return false;
+}
+
+#define CK(call)                                                   \
+  do {                                                             \
+    if (!sslsim_check(b, (call), #call)) return SSLSIM_E_CUDA;     \
+  } while (0)
+#define ENTER(b)                                  \
+  if (!(b)) return SSLSIM_E_ARG;                  \
+  if ((b)->last_error == SSLSIM_E_CUDA) return SSLSIM_E_CUDA; \
+  cudaSetDevice((b)->device)
+
+static void batch_free(WorldBatch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (World *w : b->views) delete w;
+  cudaFree(b->d_pos); cudaFree(b->d_vel); cudaFree(b->d_aux); cudaFree(b->d_cmd);
+  cudaFree(b->d_robot_ids); cudaFree(b->d_world_ids); cudaFree(b->d_gather); cudaFree(b->d_stats);
+  cudaFree(b->d_rep);
+  if (b->h_gather) cudaFreeHost(b->h_gather);
+  for (cudaEvent_t e : b->kev) cudaEventDestroy(e);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream && b->own_stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_robots, int cap_bodies, int device,
+                                uint64_t seed, uint64_t world0, int init_mode, const SslSimParams *params,
+                                bool run_init) {
+  if (!field || n_worlds <= 0 || n_robots < 0 || n_robots > SSLSIM_MAX_ROBOTS) {
+    fprintf(stderr, "sslsim_b200: new_world_batch: bad argument (n_worlds=%d, n_robots=%d, max robots %d)\n",
+            n_worlds, n_robots, SSLSIM_MAX_ROBOTS);
+    return nullptr;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "sslsim_b200: no usable CUDA device (%s); there is no CPU fallback\n",
+            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) {
+    fprintf(stderr, "sslsim_b200: device %d out of range (%d devices)\n", device, ndev);
+    return nullptr;
+  }
+  WorldBatch *b = new (std::nothrow) WorldBatch();
+  if (!b) return nullptr;
+  b->device = device; b->W = n_worlds; b->R = n_robots;
+  b->cap_bodies = cap_bodies > n_robots + 1 ? cap_bodies : n_robots + 1;
+  b->seed = seed; b->world0 = world0;
+  b->field = *field; b->field_ptr = field;
+  sslsim_derive_field(field, &b->dfield);
+  if (params) b->params = *params; else sslsim_params_default(&b->params);
+  b->robot_ids.resize(n_robots); b->robot_teams.resize(n_robots);
+  for (int i = 0; i < n_robots; ++i) { b->robot_ids[i] = i / 2; b->robot_teams[i] = (i & 1) ? TEAM_YELLOW : TEAM_BLUE; }
+  const size_t nb = (size_t)n_worlds * b->cap_bodies;
+  bool ok = sslsim_check(b, cudaSetDevice(device), "cudaSetDevice") &&
+            sslsim_check(b, cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+            sslsim_check(b, cudaEventCreate(&b->ev0), "cudaEventCreate") &&
+            sslsim_check(b, cudaEventCreate(&b->ev1), "cudaEventCreate") &&
+            sslsim_check(b, cudaMalloc(&b->d_pos, nb * sizeof(float4)), "cudaMalloc(pos)") &&
+            sslsim_check(b, cudaMalloc(&b->d_vel, nb * sizeof(float4)), "cudaMalloc(vel)") &&
+            sslsim_check(b, cudaMalloc(&b->d_aux, (size_t)n_worlds * 8 * sizeof(uint32_t)), "cudaMalloc(aux)") &&
+            sslsim_check(b, cudaMalloc(&b->d_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)") &&
+            sslsim_check(b, cudaMalloc(&b->d_robot_ids, SSLSIM_MAX_BODIES * sizeof(int)), "cudaMalloc(ids)");
+  if (ok && n_robots > 0)
+    ok = sslsim_check(b, cudaMemcpyAsync(b->d_robot_ids, b->robot_ids.data(), n_robots * sizeof(int),
+                                         cudaMemcpyHostToDevice, b->stream), "cudaMemcpy(ids)");
+  if (ok && run_init)
+    ok = sslsim_check(b, sslsim_launch_init(b->d_pos, b->d_vel, b->d_aux, n_worlds, n_robots, b->field, seed, world0,
+                                            init_mode, b->stream), "init_worlds");
+  if (ok) ok = sslsim_check(b, cudaStreamSynchronize(b->stream), "init sync");
+  if (!ok) { batch_free(b); return nullptr; }
+  return b;
+}
+
+int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total) {
+  ENTER(b);
+  if (n_steps < 0 || substeps < 0) return SSLSIM_E_ARG;
+  if (n_steps > 0 && substeps >= 0) {
+    StepArgs a;
+    a.pos = b->d_pos; a.vel = b->d_vel; a.aux = b->d_aux; a.cmd = b->cmd_active;
+    a.n_worlds = b->W; a.n_robots = b->R; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
+    a.f = b->dfield; a.p = b->params;
+    if (b->ktiming) {
+      if (b->kev_used + 2 > b->kev.size()) {
+        for (int k = 0; k < 2; ++k) {
+          cudaEvent_t ev;
+          CK(cudaEventCreate(&ev));
+          b->kev.push_back(ev);
+        }
+      }
+      CK(cudaEventRecord(b->kev[b->kev_used], b->stream));
+    }
+    CK(sslsim_launch_step(a, b->lanes, b->stream));
+    if (b->ktiming) {
+      CK(cudaEventRecord(b->kev[b->kev_used + 1], b->stream));
+      b->kev_used += 2;
+    }
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    b->timestamp += time_step_total; /* fp32 accumulator, reference src/sslsim.cpp:324 */
+    b->frame++;                      /* :325 */
+  }
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+extern "C" {
+
+void sslsim_params_default(struct SslSimParams *p) {
+  memset(p, 0, sizeof *p);
+  p->flags = 0;
+  p->solver_iterations = 10;
+  p->kick_reach = 0.015f;
+  p->kick_halfwidth = 0.04f;
+  p->kick_max_height = 0.03f;
+  p->wheel_kp = 24.0f;
+  p->wheel_fmax = 4.0f;
+  p->robot_yaw_inertia = 0.0081f;
+  p->dribble_kd = 60.0f;
+  p->dribble_cd = 8.0f;
+  p->dribble_amax = 12.0f;
+  p->dribble_reach = 0.03f;
+  p->mu_roll = 0.03f;
+}
+
+struct WorldBatch *new_world_batch(const struct FieldGeometry *field, int n_worlds, int robots_per_team, int device,
+                                   uint64_t seed) {
+  return sslsim_batch_create(field, n_worlds, 2 * robots_per_team, 0, device, seed, 0, 0, nullptr, true);
+}
+
+struct WorldBatch *new_world_batch_ex(const struct FieldGeometry *field, int n_worlds, int n_robots, int device,
+                                      uint64_t seed, uint64_t first_world_id, int init_mode,
+                                      const struct SslSimParams *params) {
+  return sslsim_batch_create(field, n_worlds, n_robots, 0, device, seed, first_world_id, init_mode, params, true);
+}
+
+void delete_world_batch(struct WorldBatch *batch) { batch_free(batch); }
+
+int world_batch_reset(struct WorldBatch *b, uint64_t seed, int init_mode) {
+  ENTER(b);
+  b->seed = seed;
+  CK(sslsim_launch_init(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->field, seed, b->world0, init_mode, b->stream));
+  b->frame = 0; b->timestamp = 0.0f;
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+int world_batch_world_count(const struct WorldBatch *b) { return b ? b->W : 0; }
+int world_batch_robot_count(const struct WorldBatch *b) { return b ? b->R : 0; }
+int world_batch_device(const struct WorldBatch *b) { return b ? b->device : -1; }
+unsigned int world_batch_frame_number(const struct WorldBatch *b) { return b ? b->frame : 0; }
+double world_batch_timestamp(const struct WorldBatch *b) { return b ? (double)b->timestamp : 0.0; }
+
+int world_batch_step(struct WorldBatch *b, int n_steps) {
+  /* reference src/sslsim.cpp:309: world_step_delta(world, 1.0 / 60, 2, 1.0 / 60 / 2) with Float = float */
+  return sslsim_batch_step(b, n_steps, 2, (float)(1.0 / 60 / 2), (float)(1.0 / 60));
+}
+
+int world_batch_step_delta(struct WorldBatch *b, int n_steps, int substeps, float fixed_time_step) {
+  return sslsim_batch_step(b, n_steps, substeps, fixed_time_step, fixed_time_step * (float)substeps);
+}
+
+int world_batch_sync(struct WorldBatch *b) {
+  ENTER(b);
+  CK(cudaStreamSynchronize(b->stream));
+  return SSLSIM_OK;
+}
+
+static int ensure_cmd_buffer(WorldBatch *b) {
+  if (!b->d_cmd && b->R > 0) CK(cudaMalloc(&b->d_cmd, (size_t)b->W * b->R * sizeof(RobotCommand)));
+  return SSLSIM_OK;
+}
+
+int world_batch_set_commands(struct WorldBatch *b, const struct RobotCommand *host_cmds) {
+  ENTER(b);
+  if (!host_cmds) { b->cmd_active = nullptr; return SSLSIM_OK; }
+  if (b->R == 0) return SSLSIM_OK;
+  int rc = ensure_cmd_buffer(b);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(b->d_cmd, host_cmds, (size_t)b->W * b->R * sizeof(RobotCommand), cudaMemcpyHostToDevice,
+                     b->stream));
+  b->cmd_active = b->d_cmd;
+  return SSLSIM_OK;
+}
+
+int world_batch_set_commands_device(struct WorldBatch *b, const struct RobotCommand *dev_cmds) {
+  ENTER(b);
+  b->cmd_active = dev_cmds;
+  return SSLSIM_OK;
+}
+
+int world_batch_clear_commands(struct WorldBatch *b) {
+  ENTER(b);
+  b->cmd_active = nullptr;
+  return SSLSIM_OK;
+}
+
+int world_batch_gen_commands(struct WorldBatch *b, uint64_t period, int kind) {
+  ENTER(b);
+  if (b->R == 0) return SSLSIM_OK;
+  int rc = ensure_cmd_buffer(b);
+  if (rc) return rc;
+  CK(sslsim_launch_gen_commands(b->d_cmd, b->W, b->R, b->seed, b->world0, period, kind, b->stream));
+  b->cmd_active = b->d_cmd;
+  return SSLSIM_OK;
+}
+
+static int ensure_rep(WorldBatch *b, size_t bytes) {
+  if (bytes > b->rep_cap) {
+    CK(cudaStreamSynchronize(b->stream));
+    cudaFree(b->d_rep); b->d_rep = nullptr; b->rep_cap = 0;
+    size_t cap = bytes < 4096 ? 4096 : bytes * 2;
+    CK(cudaMalloc(&b->d_rep, cap));
+    b->rep_cap = cap;
+  }
+  return SSLSIM_OK;
+}
+
+int world_batch_replace_robots(struct WorldBatch *b, const struct RobotReplacement *recs, int n) {
+  ENTER(b);
+  if (n < 0 || (n > 0 && !recs)) return SSLSIM_E_ARG;
+  if (n == 0) return SSLSIM_OK;
+  int rc = ensure_rep(b, (size_t)n * sizeof(RobotReplacement));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(b->d_rep, recs, (size_t)n * sizeof(RobotReplacement), cudaMemcpyHostToDevice, b->stream));
+  CK(sslsim_launch_replace_robots(b->d_pos, b->W, b->R, (const RobotReplacement *)b->d_rep, n, b->stream));
+  CK(cudaStreamSynchronize(b->stream)); /* the staging buffer is reused by the next call */
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+int world_batch_replace_balls(struct WorldBatch *b, const struct BallReplacement *recs, int n) {
+  ENTER(b);
+  if (n < 0 || (n > 0 && !recs)) return SSLSIM_E_ARG;
+  if (n == 0) return SSLSIM_OK;
+  int rc = ensure_rep(b, (size_t)n * sizeof(BallReplacement));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(b->d_rep, recs, (size_t)n * sizeof(BallReplacement), cudaMemcpyHostToDevice, b->stream));
+  CK(sslsim_launch_replace_balls(b->d_pos, b->d_vel, b->W, b->R, (const BallReplacement *)b->d_rep, n, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+int world_batch_read_state(struct WorldBatch *b, float *pos, float *vel, uint32_t *aux) {
+  ENTER(b);
+  const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4);
+  if (pos) CK(cudaMemcpyAsync(pos, b->d_pos, nb, cudaMemcpyDeviceToHost, b->stream));
+  if (vel) CK(cudaMemcpyAsync(vel, b->d_vel, nb, cudaMemcpyDeviceToHost, b->stream));
+  if (aux) CK(cudaMemcpyAsync(aux, b->d_aux, (size_t)b->W * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return SSLSIM_OK;
+}
+
+int world_batch_read_aux(struct WorldBatch *b, uint32_t *aux) { return world_batch_read_state(b, nullptr, nullptr, aux); }
+
+int world_batch_write_state(struct WorldBatch *b, const float *pos, const float *vel, const uint32_t *aux) {
+  ENTER(b);
+  const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4);
+  if (pos) CK(cudaMemcpyAsync(b->d_pos, pos, nb, cudaMemcpyHostToDevice, b->stream));
+  if (vel) CK(cudaMemcpyAsync(b->d_vel, vel, nb, cudaMemcpyHostToDevice, b->stream));
+  if (aux) CK(cudaMemcpyAsync(b->d_aux, aux, (size_t)b->W * 8 * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+int world_batch_device_state(struct WorldBatch *b, void **pos, void **vel, void **aux, void **cmd) {
+  if (!b) return SSLSIM_E_ARG;
+  if (pos) *pos = b->d_pos;
+  if (vel) *vel = b->d_vel;
+  if (aux) *aux = b->d_aux;
+  if (cmd) *cmd = (void *)b->cmd_active;
+  return SSLSIM_OK;
+}
+
+size_t world_batch_detection_record_size(const struct WorldBatch *b) {
+  return b ? (size_t)(6 + 7 * b->R) * sizeof(float) : 0;
+}
+
+int world_batch_gather_detections(struct WorldBatch *b, const int *world_ids, int n, void *out, size_t capacity) {
+  ENTER(b);
+  if (n < 0 || (n > 0 && (!world_ids || !out))) return SSLSIM_E_ARG;
+  const size_t rec = world_batch_detection_record_size(b);
+  if ((size_t)n * rec > capacity) return SSLSIM_E_SPACE;
+  if (n == 0) return 0;
+  if (n > b->gather_cap) {
+    CK(cudaStreamSynchronize(b->stream));
+    cudaFree(b->d_world_ids); cudaFree(b->d_gather);
+    if (b->h_gather) cudaFreeHost(b->h_gather);
+    b->d_world_ids = nullptr; b->d_gather = nullptr; b->h_gather = nullptr; b->gather_cap = 0;
+    const int cap = n < 64 ? 64 : n;
+    CK(cudaMalloc(&b->d_world_ids, (size_t)cap * sizeof(int)));
+    CK(cudaMalloc(&b->d_gather, (size_t)cap * rec));
+    CK(cudaMallocHost(&b->h_gather, (size_t)cap * rec));
+    b->gather_cap = cap;
+  }
+  CK(cudaMemcpyAsync(b->d_world_ids, world_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  CK(sslsim_launch_gather(b->d_pos, b->W, b->R, b->d_world_ids, n, b->d_robot_ids, b->d_gather, b->stream));
+  CK(cudaMemcpyAsync(b->h_gather, b->d_gather, (size_t)n * rec, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  memcpy(out, b->h_gather, (size_t)n * rec);
+  return (int)((size_t)n * rec);
+}
+
+int world_batch_reduce_stats(struct WorldBatch *b, struct BatchStats *out) {
+  ENTER(b);
+  if (!out) return SSLSIM_E_ARG;
+  CK(sslsim_launch_reduce(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->world0, b->d_stats, b->stream));
+  unsigned long long h[8];
+  CK(cudaMemcpyAsync(h, b->d_stats, sizeof h, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  out->goals_blue = h[0]; out->goals_yellow = h[1]; out->ball_out = h[2]; out->kicks = h[3];
+  out->touches = h[4]; out->contacts = h[5]; out->bad_worlds = h[6]; out->checksum = h[7];
+  return SSLSIM_OK;
+}
+
+void *world_batch_stream(struct WorldBatch *b) { return b ? (void *)b->stream : nullptr; }
+
+int world_batch_set_stream(struct WorldBatch *b, void *cuda_stream) {
+  ENTER(b);
+  CK(cudaStreamSynchronize(b->stream));
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  b->stream = (cudaStream_t)cuda_stream;
+  b->own_stream = false;
+  return SSLSIM_OK;
+}
+
+int world_batch_timer_start(struct WorldBatch *b) {
+  ENTER(b);
+  CK(cudaEventRecord(b->ev0, b->stream));
+  return SSLSIM_OK;
+}
+
+int world_batch_timer_stop(struct WorldBatch *b, float *elapsed_ms) {
+  ENTER(b);
+  CK(cudaEventRecord(b->ev1, b->stream));
+  CK(cudaEventSynchronize(b->ev1));
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return SSLSIM_OK;
+}
+
+int world_batch_enable_kernel_timing(struct WorldBatch *b, int on) {
+  ENTER(b);
+  b->ktiming = on != 0;
+  return SSLSIM_OK;
+}
+
+int world_batch_kernel_time(struct WorldBatch *b, float *total_ms, int *launches, int reset) {
+  ENTER(b);
+  CK(cudaStreamSynchronize(b->stream));
+  float tot = 0.0f;
+  for (size_t k = 0; k + 1 < b->kev_used; k += 2) {
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, b->kev[k], b->kev[k + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)(b->kev_used / 2);
+  if (reset) b->kev_used = 0;
+  return SSLSIM_OK;
+}
+
+int world_batch_set_lanes_per_world(struct WorldBatch *b, int lanes) {
+  if (!b) return SSLSIM_E_ARG;
+  if (lanes != 0 && lanes != 16 && lanes != 32) return SSLSIM_E_ARG;
+  if (lanes == 16 && b->R + 1 > 16) return SSLSIM_E_ARG;
+  b->lanes = lanes;
+  return SSLSIM_OK;
+}
+
+int world_batch_last_error(const struct WorldBatch *b) { return b ? b->last_error : SSLSIM_E_ARG; }
+const char *world_batch_error_string(const struct WorldBatch *b) { return b ? b->errstr : "null batch"; }
+const char *sslsim_b200_version(void) { return "sslsim_b200 0.1 (sm_100a)"; }
+
+} /* extern "C" */

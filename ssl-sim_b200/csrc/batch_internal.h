@@ -1,0 +1,73 @@
+/*
+ * batch_internal.h -- host-side objects behind the C ABI (not public).
+ */
+#ifndef SSLSIM_B200_BATCH_INTERNAL_H
+#define SSLSIM_B200_BATCH_INTERNAL_H
+#include <vector>
+#include "dev_types.h"
+
+#define SSLSIM_LEGACY_MAX_ROBOTS 100 /* reference src/sslsim.cpp:215 stack_vector<Robot,100> */
+#define SSLSIM_LEGACY_MAX_BALLS 20   /* reference src/sslsim.cpp:214 */
+#define SSLSIM_MAX_BODIES 32
+
+struct World;
+
+/* interior-pointer handles, stable for the world's lifetime (reference src/sslsim.cpp:334-356) */
+struct Robot { World *world; int index; int id; enum Team team; };
+struct Ball { World *world; int index; };
+
+struct WorldBatch {
+  int device = 0, W = 0, R = 0;
+  int cap_bodies = 0; /* allocated bodies per world (>= R+1; 32 for a growable legacy world) */
+  uint64_t seed = 0, world0 = 0;
+  FieldGeometry field{};
+  const FieldGeometry *field_ptr = nullptr; /* the caller's (borrowed) pointer, returned by world_get_field */
+  DevField dfield{};
+  SslSimParams params{};
+  float4 *d_pos = nullptr, *d_vel = nullptr;
+  uint32_t *d_aux = nullptr;
+  RobotCommand *d_cmd = nullptr;          /* owned command buffer (lazy) */
+  const RobotCommand *cmd_active = nullptr; /* what the step kernel reads; NULL = passive robots */
+  int *d_robot_ids = nullptr;
+  int *d_world_ids = nullptr; float *d_gather = nullptr; int gather_cap = 0;
+  float *h_gather = nullptr; /* pinned */
+  unsigned long long *d_stats = nullptr;
+  void *d_rep = nullptr; size_t rep_cap = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ktiming = false;
+  std::vector<cudaEvent_t> kev; /* pairs around step launches */
+  size_t kev_used = 0;
+  unsigned int frame = 0;
+  float timestamp = 0.0f;
+  int lanes = 0;
+  int last_error = 0;
+  char errstr[256] = {0};
+  std::vector<int> robot_ids; /* per robot slot */
+  std::vector<int> robot_teams;
+  std::vector<World *> views;
+};
+
+struct World {
+  WorldBatch *batch = nullptr;
+  int index = 0;
+  bool owns_batch = false;
+  Robot robots[SSLSIM_LEGACY_MAX_ROBOTS];
+  int n_robots = 0;
+  Ball balls[SSLSIM_LEGACY_MAX_BALLS];
+  int n_balls = 1;
+  /* host mirror of this world's device state */
+  float pos[SSLSIM_MAX_BODIES][4];
+  float vel[SSLSIM_MAX_BODIES][4];
+  uint32_t aux[8];
+  bool mirror_valid = false;
+  float local_time = 0.0f; /* Bullet's stepSimulation accumulator (m_localTime) */
+};
+
+bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what);
+WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_robots, int cap_bodies, int device,
+                                uint64_t seed, uint64_t world0, int init_mode, const SslSimParams *params,
+                                bool run_init);
+int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total);
+#endif

@@ -1,0 +1,48 @@
+/*
+ * dev_types.h -- internal types shared by the kernels and the host C-ABI layer.
+ * Not part of the public boundary (include/ is).
+ */
+#ifndef SSLSIM_B200_DEV_TYPES_H
+#define SSLSIM_B200_DEV_TYPES_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sslsim_batch.h"
+
+/* Field geometry derived once on the host from struct FieldGeometry
+ * (reference src/field.h:18-42, solids built at src/sslsim.cpp:145-203) and
+ * passed to every kernel by value, i.e. through the constant bank. */
+struct DevField {
+  float half_len, half_wid, limit_x, limit_y;
+  float goal_half_w, goal_back, goal_height;
+  float goal_reach_y; /* goal_width/2 + goal_wall_width: |y| extent of the goal solids */
+  float lo[6][3], hi[6][3]; /* 6 goal boxes: -x goal {side -y, side +y, rear}, +x goal mirrored */
+};
+
+struct StepArgs {
+  float4 *pos;   /* [W][R+1] {x,y,z,yaw}; ball (last): {x,y,z,omega_x} */
+  float4 *vel;   /* [W][R+1] {vx,vy,vz,yaw rate}; ball: {vx,vy,vz,omega_y} */
+  uint32_t *aux; /* [W][8] */
+  const RobotCommand *cmd; /* [W][R] or NULL */
+  int n_worlds, n_robots, n_steps, substeps;
+  float h;
+  DevField f;
+  SslSimParams p;
+};
+
+void sslsim_derive_field(const FieldGeometry *g, DevField *d);
+
+/* kernel launchers (kernels.cu / step_kernel.cu) */
+cudaError_t sslsim_launch_step(const StepArgs &a, int lanes_per_world, cudaStream_t s);
+cudaError_t sslsim_launch_init(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots,
+                               const FieldGeometry &g, uint64_t seed, uint64_t world0, int mode, cudaStream_t s);
+cudaError_t sslsim_launch_gen_commands(RobotCommand *cmd, int n_worlds, int n_robots, uint64_t seed,
+                                       uint64_t world0, uint64_t period, int kind, cudaStream_t s);
+cudaError_t sslsim_launch_replace_robots(float4 *pos, int n_worlds, int n_robots, const RobotReplacement *recs,
+                                         int n, cudaStream_t s);
+cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, int n_worlds, int n_robots,
+                                        const BallReplacement *recs, int n, cudaStream_t s);
+cudaError_t sslsim_launch_gather(const float4 *pos, int n_worlds, int n_robots, const int *world_ids, int n,
+                                 const int *robot_ids, float *out, cudaStream_t s);
+cudaError_t sslsim_launch_reduce(const float4 *pos, const float4 *vel, const uint32_t *aux, int n_worlds,
+                                 int n_robots, uint64_t world0, unsigned long long *out8, cudaStream_t s);
+#endif
