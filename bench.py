@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- world-steps/sec of the batched SSL world-stepper (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): 4,096 batched 6v6 worlds per GPU on
+FIELD_2015 with randomized wheel-velocity commands that are redrawn every 30 world-steps.
+One bench *step* = one command batch + 30 world-steps of every world = ONE launch of the
+fused `step_worlds` kernel.  One world-step = one `world_step` of the reference
+(reference src/sslsim.cpp:307-310: 1/60 s, two 1/120 s substeps).
+
+  value     device-resident arm: the K command batches are staged in HBM before the timed region;
+            each step is timed with CUDA events on the batch's own stream; L2 is flushed between
+            steps (outside the per-step event pairs).
+  e2e       the same work through the C ABI with HOST buffers: per step the command batch is copied
+            from pinned host memory (world_batch_set_commands), stepped, and the per-world event /
+            statistics words are read back (world_batch_read_aux); wall time of K steps.
+  roofline  algorithmic bytes (1,232 B per 6v6 world-step) / kernel duration vs the
+            measured HBM copy bandwidth.
+  cpu_baseline  the CPU oracle (restated-Bullet port; Bullet itself is not buildable here) on the
+            host cores for a bounded sample of the same workload.
+
+`--impl reference` times that CPU oracle alone (rank 0 only) on the same config.
+Multi-GPU: one process per GPU (torchrun), contiguous world ranges, no per-step collective; one
+NCCL all-gather of the episode statistics at the end of the timed region.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORLD_STEPS_PER_STEP = 30      # commands are redrawn every 30 world-steps
+SETTLE_STEPS = 120             # drop from 0.5 m and settle before timing (2 s of sim time)
+SEED = 0x5351
+
+
+def bytes_per_world_step(R):
+    """state read + write (32 B per body each way), command read (32 B per robot), aux RMW."""
+    return 2 * 32 * (R + 1) + 32 * R + 16
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(R, sample_worlds, target_seconds, threads):
+    """world-steps/s of the CPU oracle on a bounded sample of the workload (cpu_baseline leg)."""
+    import oracle_binding as ob
+    ob.build()
+    w = ob.Worlds(sample_worlds, R, seed=SEED)
+    w.gen_commands(0, 0)
+    w.step(SETTLE_STEPS, threads=threads)
+    period, done, t0 = 1, 0, time.perf_counter()
+    while True:
+        w.gen_commands(period, 0)
+        w.step(WORLD_STEPS_PER_STEP, threads=threads)
+        period += 1
+        done += sample_worlds * WORLD_STEPS_PER_STEP
+        el = time.perf_counter() - t0
+        if el >= target_seconds:
+            return done / el, el, period - 1
+
+
+def run_reference(args, rank, world_size):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+    Bullet (the reference's step, src/sslsim.cpp:323) cannot be built here, so this is the
+    restated-Bullet CPU oracle (kind "port") with every host thread, on the bench config."""
+    if rank != 0:
+        return
+    import oracle_binding as ob
+    ob.build()
+    threads = os.cpu_count() or 1
+    R = args.robots
+    sample = min(args.worlds, args.ref_sample_worlds)
+    w = ob.Worlds(sample, R, seed=SEED)
+    w.gen_commands(0, 0)
+    w.step(SETTLE_STEPS, threads=threads)
+    for k in range(args.warmup):
+        w.gen_commands(1 + k, 0)
+        w.step(WORLD_STEPS_PER_STEP, threads=threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        w.gen_commands(1 + args.warmup + k, 0)
+        w.step(WORLD_STEPS_PER_STEP, threads=threads)
+    el = time.perf_counter() - t0
+    value = sample * WORLD_STEPS_PER_STEP * args.steps / el
+    line = {
+        "impl": "reference", "metric": "world-steps/sec (6v6, 60 Hz)", "value": value, "unit": "world-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": el * 1e3 / args.steps * (args.worlds / sample), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, world_size),
+        "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d worlds x %d world-steps per step, %d steps; restated-Bullet CPU oracle "
+                                   "(oracle/ssl_oracle.c), Bullet itself not buildable here" %
+                                   (sample, args.worlds, WORLD_STEPS_PER_STEP, args.steps)},
+        "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, world_size):
+    return {"workload": "configs[1]: %d batched %dv%d worlds per GPU, FIELD_2015, randomized wheel-velocity "
+                        "commands redrawn every %d world-steps; 1 bench step = %d world-steps of every world"
+                        % (args.worlds, args.robots // 2, args.robots // 2, WORLD_STEPS_PER_STEP, WORLD_STEPS_PER_STEP),
+            "worlds_per_gpu": args.worlds, "robots_per_world": args.robots,
+            "world_steps_per_step": WORLD_STEPS_PER_STEP, "substeps_per_world_step": 2,
+            "total_worlds": args.worlds * world_size, "sharding": "contiguous world ranges, no per-step collective",
+            "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs); "
+                  "working set %.1f MiB < L2" % (args.worlds * (bytes_per_world_step(args.robots) - 16 + 32) / 2 ** 20)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU (configs[1]: 4096)")
+    ap.add_argument("--robots", type=int, default=12, help="robots per world (6v6 = 12)")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per world: 16, 32 or 0 = auto")
+    ap.add_argument("--ref-sample-worlds", type=int, default=512)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    sim = importlib.import_module("ssl-sim_b200")
+    sim.lib()  # fails loudly if the CUDA library is missing: there is no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world_size > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, R, K, WU = args.worlds, args.robots, args.steps, args.warmup
+    N = R + 1
+    bpws = bytes_per_world_step(R)
+    first_world, _ = sim.shard_range(W * world_size, rank, world_size)   # contiguous range per GPU
+    b = sim.WorldBatch(W, R, device=local_rank, seed=SEED, first_world_id=first_world)
+    if args.lanes:
+        b.set_lanes_per_world(args.lanes)
+    # stage every command batch (warm-up + timed) in HBM before the timed region
+    cmd_bytes = W * R * 32
+    n_sets = WU + K
+    stage = torch.empty(n_sets * cmd_bytes, dtype=torch.uint8, device=dev)
+    for k in range(n_sets):
+        b.gen_commands_into(stage.data_ptr() + k * cmd_bytes, 1 + k, 0)
+    b.gen_commands(0, 0)
+    b.step(SETTLE_STEPS)
+    b.sync()
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        b.sync()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def allgather_stats():
+        _, tot = sim.allgather_stats(b.reduce_stats(), device=dev)
+        return tot
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    for k in range(WU):
+        b.set_commands_device(stage.data_ptr() + k * cmd_bytes)
+        b.step(WORLD_STEPS_PER_STEP)
+        flush.zero_()
+    allgather_stats()  # warms the NCCL communicator up
+    torch.cuda.synchronize()
+    b.enable_kernel_timing(True)
+    b.kernel_time(reset=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        b.set_commands_device(stage.data_ptr() + (WU + k) * cmd_bytes)
+        b.step(WORLD_STEPS_PER_STEP)   # events bracket this launch on the batch's stream
+        b.sync()
+        flush.zero_()                   # L2 flush, outside the event pair
+        torch.cuda.synchronize()
+    total_stats = allgather_stats()
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.finish()
+    kern_ms, launches = b.kernel_time(reset=True)
+    b.enable_kernel_timing(False)
+    assert launches == K
+    t = torch.tensor([kern_ms, wall_s * 1e3], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kern_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    units = W * world_size * WORLD_STEPS_PER_STEP * K
+    value = units / (kern_ms_max * 1e-3)
+
+    # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_host = min(n_sets, 16)
+        host_cmd = torch.empty(n_host * cmd_bytes, dtype=torch.uint8).pin_memory()
+        host_cmd.copy_(stage[: n_host * cmd_bytes].cpu())
+        host_aux = torch.empty(W * 8, dtype=torch.int32).pin_memory()
+        hp, ap_ = host_cmd.data_ptr(), host_aux.data_ptr()
+        L, h = sim.lib(), b._h
+
+        def e2e_step(k):
+            L.world_batch_set_commands(h, C.c_void_p(hp + (k % n_host) * cmd_bytes))   # H2D, pinned
+            L.world_batch_step(h, WORLD_STEPS_PER_STEP)
+            rc = L.world_batch_read_aux(h, C.c_void_p(ap_))                            # D2H + sync
+            if rc < 0:
+                raise RuntimeError("e2e step failed: %d" % rc)
+        for k in range(WU):
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            e2e_step(WU + k)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": units / float(te[0]), "unit": "world-steps/s", "h2d_bytes_per_step": cmd_bytes,
+               "d2h_bytes_per_step": W * 32, "ms_per_step": float(te[0]) * 1e3 / K,
+               "api": "world_batch_set_commands(host) + world_batch_step(30) + world_batch_read_aux(host)"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, el, reps = cpu_oracle_rate(R, min(W, args.ref_sample_worlds), args.cpu_seconds, threads)
+        cpu = {"value": v, "unit": "world-steps/s", "cores": threads, "kind": "port",
+               "sample": "%d worlds x %d world-steps x %d command batches in %.1f s; restated-Bullet CPU oracle "
+                         "(oracle/ssl_oracle.c, -O2, pthreads); Bullet itself is not buildable here (SURVEY 8c)"
+                         % (min(W, args.ref_sample_worlds), WORLD_STEPS_PER_STEP, reps, el)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_launch_bytes = bpws * W * WORLD_STEPS_PER_STEP
+        per_launch_s = kern_ms_max * 1e-3 / K
+        achieved = per_launch_bytes / per_launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "world-steps/sec (6v6, 60 Hz)", "value": value, "unit": "world-steps/s",
+            "n_gpus": world_size, "steps": K, "warmup": WU, "ms_per_step": kern_ms_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args, world_size),
+            "wall_ms_per_step_incl_l2_flush": wall_ms_max / K,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": K + 1,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "step_worlds", "algorithmic_bytes_per_launch": per_launch_bytes,
+                         "bytes_per_world_step": bpws, "kernel_ms_per_launch": kern_ms_max / K,
+                         "note": "latency/issue-bound fused kernel: state stays in registers for the 30 "
+                                 "world-steps of a launch; see DESIGN.md"},
+            "cpu_baseline": cpu,
+            "episode_stats": total_stats,
+        }
+        print(json.dumps(line), flush=True)
+    b.close()
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

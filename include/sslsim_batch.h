@@ -136,6 +136,9 @@ int world_batch_clear_commands(struct WorldBatch *batch);
  * speeds U[-40,40] rad/s, kind 1 = kind 0 + spinner + kicks; keyed
  * (seed, world id, robot, period). */
 int world_batch_gen_commands(struct WorldBatch *batch, uint64_t period, int kind);
+/* same generator, written to a caller-owned device buffer (n_worlds * n_robots records)
+ * without installing it: pre-stages command sets that set_commands_device then selects */
+int world_batch_gen_commands_into(struct WorldBatch *batch, struct RobotCommand *dev_out, uint64_t period, int kind);
 
 /* ---- replacement input: robot_set_pos / ball_set_vec (src/robot.h:23,
  * src/ball.h:19) as a sparse device scatter (K2). */

@@ -112,6 +112,7 @@ BATCH_SYMBOLS = [
     ("world_batch_sync", _I, [_VP]),
     ("world_batch_set_commands", _I, [_VP, _VP]), ("world_batch_set_commands_device", _I, [_VP, _VP]),
     ("world_batch_clear_commands", _I, [_VP]), ("world_batch_gen_commands", _I, [_VP, _U64, _I]),
+    ("world_batch_gen_commands_into", _I, [_VP, _VP, _U64, _I]),
     ("world_batch_replace_robots", _I, [_VP, _VP, _I]), ("world_batch_replace_balls", _I, [_VP, _VP, _I]),
     ("world_batch_read_state", _I, [_VP, _VP, _VP, _VP]), ("world_batch_write_state", _I, [_VP, _VP, _VP, _VP]),
     ("world_batch_read_aux", _I, [_VP, _VP]),
@@ -236,6 +237,12 @@ class WorldBatch:
 
     def gen_commands(self, period, kind=0):
         self._ck(lib().world_batch_gen_commands(self._h, period, kind))
+
+    def gen_commands_into(self, dev_ptr, period, kind=0):
+        self._ck(lib().world_batch_gen_commands_into(self._h, C.c_void_p(dev_ptr), period, kind))
+
+    def set_commands_device(self, dev_ptr):
+        self._ck(lib().world_batch_set_commands_device(self._h, C.c_void_p(dev_ptr)))
 
     def replace_robots(self, recs):
         recs = np.ascontiguousarray(recs, dtype=ROBOT_REPLACEMENT_DTYPE)
@@ -388,3 +395,6 @@ class World:
     def ball_vec(self):
         v = lib().ball_get_vec(self.ball())
         return (v.x, v.y, v.z)
+
+
+from .sharding import STAT_KEYS, allgather_stats, shard_range  # noqa: E402,F401

@@ -266,6 +266,13 @@ int world_batch_gen_commands(struct WorldBatch *b, uint64_t period, int kind) {
   return SSLSIM_OK;
 }
 
+int world_batch_gen_commands_into(struct WorldBatch *b, struct RobotCommand *dev_out, uint64_t period, int kind) {
+  ENTER(b);
+  if (!dev_out) return SSLSIM_E_ARG;
+  CK(sslsim_launch_gen_commands(dev_out, b->W, b->R, b->seed, b->world0, period, kind, b->stream));
+  return SSLSIM_OK;
+}
+
 static int ensure_rep(WorldBatch *b, size_t bytes) {
   if (bytes > b->rep_cap) {
     CK(cudaStreamSynchronize(b->stream));

@@ -298,3 +298,24 @@ def test_full_size_properties(sim):
     ss = s.read_state()
     for k in range(3):
         np.testing.assert_array_equal(ss[k], sa[k][1000:1064])
+
+
+def test_c_client_runs_like_reference_cli(sim, orc, tmp_path):
+    """tests/c_api_client.c (the reference CLI's call sequence, src/main.c:62-96) against the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "c_api_client"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c_api_client.c"), "-o", str(exe), sim.LIB_PATH,
+                    "-Wl,-rpath," + os.path.dirname(sim.LIB_PATH)], check=True)
+    out = subprocess.run([str(exe), "90"], check=True, capture_output=True, text=True).stdout.splitlines()
+    o = orc.Worlds(1, 12)
+    o.step(90)
+    assert out[0].startswith("frame 90 ")
+    ball = [np.float32(v) for v in out[1].split()[1:]]
+    assert ball == list(o.pos[0, 12, :3])
+    for i in range(12):
+        f = out[2 + i].split()
+        assert (int(f[1]), int(f[2])) == (i // 2, i % 2)
+        assert [np.float32(v) for v in f[3:]] == list(o.pos[0, i, [0, 1, 3]])

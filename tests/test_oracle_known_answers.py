@@ -1,0 +1,200 @@
+"""CPU tests that pin the oracle (oracle/ssl_oracle.c) to analytic known answers derived from the
+reference's scene constants (reference src/sslsim.cpp:17-28, 47, 87, 141, 240; src/field.c:47-63).
+
+The reference ships no tests or golden vectors and its step is un-vendored Bullet (SURVEY 8c:
+"parity unpinned"), so these closed-form checks are what anchors the oracle.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+G = np.float32(9.80665)
+H = np.float32(1.0 / 60 / 2)
+
+
+def _one_world(orc, R=0, **kw):
+    w = orc.Worlds(1, R, **kw)
+    return w
+
+
+def test_free_fall_semi_implicit_euler(orc):
+    """Ball dropped from 0.5 m (reference src/sslsim.cpp:22, :251): v -= g h, z += v h each 1/120 s substep."""
+    w = _one_world(orc)
+    z, v = np.float32(0.5), np.float32(0.0)
+    for n in range(30):
+        w.step(1, substeps=1)
+        v = np.float32(v + (np.float32(0.0) - np.float32(G * H)))
+        z = np.float32(z + np.float32(v * H))
+        assert w.vel[0, 0, 2] == v and w.pos[0, 0, 2] == z, n
+    # closed form: z_n = 0.5 - g h^2 n(n+1)/2
+    assert abs(float(z) - (0.5 - 9.80665 * float(H) ** 2 * 30 * 31 / 2)) < 1e-5
+
+
+def test_ball_first_bounce_restitution_half(orc):
+    """ball (0.5) x ground (1.0) restitution by Bullet's product rule -> rebound speed = 0.5 x impact speed."""
+    w = _one_world(orc)
+    prev_v = 0.0
+    for n in range(200):
+        w.step(1, substeps=1)
+        v = float(w.vel[0, 0, 2])
+        if v > 0:
+            break
+        prev_v = v
+    assert prev_v < -2.5            # sqrt(2 g 0.48) ~ 3.07 m/s
+    assert v == pytest.approx(-0.5 * prev_v, rel=0.03)
+
+
+def test_robot_first_bounce_restitution(orc):
+    """robot (0.2) x ground (1.0) -> 0.2, plus Bullet's ERP term (0.2 x penetration / h) when the robot
+    is first seen already penetrating (robots get no predictive contact: only the ball has CCD upstream,
+    src/sslsim.cpp:58-59)."""
+    w = _one_world(orc, R=1)
+    prev_v, prev_z = 0.0, 0.5
+    for n in range(200):
+        w.step(1, substeps=1)
+        v = float(w.vel[0, 0, 2])
+        if v > 0:
+            break
+        prev_v, prev_z = v, float(w.pos[0, 0, 2])
+    dist = prev_z - 0.025
+    expect = -0.2 * prev_v + (0.2 * -dist / float(H) if dist <= 0 else 0.0)
+    assert prev_v < -2.5
+    assert v == pytest.approx(expect, rel=1e-4)
+
+
+def test_rest_heights(orc):
+    """ball rests at its radius 0.0215 (src/sslsim.cpp:17), the robot origin at the wheel radius 0.025 (:23)."""
+    w = _one_world(orc, R=2)
+    w.pos[0, 1, :2] = (2.0, 2.0)
+    w.pos[0, 0, :2] = (-2.0, -2.0)
+    w.step(600)
+    assert abs(float(w.pos[0, 2, 2]) - 0.0215) < 1e-4
+    assert abs(float(w.pos[0, 0, 2]) - 0.025) < 1e-4 and abs(float(w.pos[0, 1, 2]) - 0.025) < 1e-4
+    assert np.abs(w.vel[0, :, :3]).max() < 1e-3
+
+
+def test_sliding_friction_and_no_spin(orc):
+    """Zero inertia upstream (src/sslsim.cpp:46) => the ball slides with mu g = 0.25 x 9.80665 and never spins."""
+    w = _one_world(orc)
+    w.pos[0, 0, 2] = 0.0215
+    w.vel[0, 0, 0] = 2.0
+    w.step(30)   # 0.5 s
+    assert float(w.vel[0, 0, 0]) == pytest.approx(2.0 - 0.25 * 9.80665 * 0.5, abs=2e-3)
+    assert w.pos[0, 0, 3] == 0 and w.vel[0, 0, 3] == 0
+    w.step(60)
+    assert abs(float(w.vel[0, 0, 0])) < 1e-3       # stopped: 2 / 2.4517 = 0.816 s
+    assert float(w.pos[0, 0, 0]) == pytest.approx(2.0 ** 2 / (2 * 0.25 * 9.80665), abs=0.02)
+
+
+def test_ball_spin_model_rolls(orc):
+    """Builder-defined rolling model: sliding turns into rolling at 5/7 v0, then decays with mu_roll g."""
+    p = orc.default_params(flags=orc.F_BALL_SPIN)
+    w = orc.Worlds(1, 0, params=p)
+    w.pos[0, 0, 2] = 0.0215
+    w.vel[0, 0, 0] = 2.0
+    w.step(40)
+    vx, wy = float(w.vel[0, 0, 0]), float(w.vel[0, 0, 3])
+    assert vx == pytest.approx(wy * 0.0215, rel=2e-2)       # rolling without slipping: v = omega r
+    assert 1.2 < vx < 2.0 * 5 / 7 + 0.01
+
+
+def test_walls_and_field_limits(orc):
+    """FIELD_2015 walls at +-5.2 / +-3.7 (src/field.h:36-42, src/field.c:47-63)."""
+    w = _one_world(orc, R=2)
+    w.pos[0, 0] = (4.5, 2.0, 0.025, 0.0); w.vel[0, 0, 0] = 5.0
+    w.pos[0, 1] = (0.0, -3.0, 0.025, 0.0); w.vel[0, 1, 1] = -5.0
+    w.pos[0, 2] = (0.0, 3.0, 0.0215, 0.0); w.vel[0, 2, 1] = 6.0
+    mx = my = by = 0.0
+    bounced = False
+    for _ in range(120):
+        w.step(1)
+        bounced |= float(w.vel[0, 2, 1]) < -1.0
+        mx = max(mx, float(w.pos[0, 0, 0])); my = min(my, float(w.pos[0, 1, 1])); by = max(by, float(w.pos[0, 2, 1]))
+    assert 5.2 - 0.09 - 0.02 < mx < 5.2 - 0.09 + 5e-3
+    assert -(3.7 - 0.09) - 5e-3 < my < -(3.7 - 0.09) + 0.02
+    assert 3.7 - 0.0215 - 0.08 < by < 3.7 - 0.0215 + 5e-3   # reflects within one substep of travel (6 m/s x 1/120 s) of the wall
+    assert bounced     # came back off the wall (e = 0.5)
+
+
+def test_goal_and_out_events(orc):
+    w = orc.Worlds(2, 0)
+    w.pos[:, 0, 2] = 0.0215
+    w.pos[0, 0, :2] = (4.0, 0.1); w.vel[0, 0, 0] = 4.0      # into the +x goal
+    w.pos[1, 0, :2] = (-4.0, 1.5); w.vel[1, 0, 0] = -4.0     # past the -x goal line beside the goal: out
+    seen = [0, 0]
+    for _ in range(120):
+        w.step(1)
+        for k in range(2):
+            seen[k] |= int(w.aux[k, 0]) & (0xF << 12)
+    assert seen[0] & (1 << 12) and not seen[0] & (1 << 14)
+    assert seen[1] & (1 << 14) and not seen[1] & (3 << 12)
+    assert int(w.aux[0, 4]) == 1 and int(w.aux[1, 5]) & 0xFFFF == 1
+    # the goal's rear wall (e = 0: goal bodies keep Bullet's default restitution) stops the ball inside the goal
+    assert 4.5 < float(w.pos[0, 0, 0]) < 4.5 + 0.18 and abs(float(w.vel[0, 0, 0])) < 0.05
+
+
+def test_kick_and_touch_bookkeeping(orc):
+    w = orc.Worlds(1, 2)
+    w.pos[0, 0] = (0.0, 0.0, 0.025, 0.0)
+    w.pos[0, 1] = (2.0, 0.0, 0.025, np.pi)
+    w.pos[0, 2] = (0.115, 0.0, 0.0215, 0.0)
+    w.cmd = np.zeros((1, 2), orc.CMD_DTYPE)
+    w.cmd[0, 0]["kickspeedx"] = 3.0
+    w.step(1)
+    assert int(w.aux[0, 0]) & (1 << 15) and int(w.aux[0, 0]) & 0xFF == 0 and int(w.aux[0, 5]) >> 16 == 1
+    peak = np.frombuffer(w.aux[0, 1:2].tobytes(), np.float32)[0]
+    assert peak == pytest.approx(9.0, rel=1e-3)
+    w.cmd[0, 0]["kickspeedx"] = 0.0
+    touched = 0
+    for _ in range(80):
+        w.step(1)
+        touched |= int(w.aux[0, 2])
+    assert touched & 2 and int(w.aux[0, 0]) & 0xFF == 1     # the ball reached robot 1 and touched it
+    assert int(w.aux[0, 6]) >= 1
+
+
+def test_wheel_drive_moves_robot(orc):
+    """velocity-mode command (veltangent) accelerates the robot along its heading; yaw rate follows velangular."""
+    w = orc.Worlds(1, 1)
+    w.pos[0, 0] = (0.0, 0.0, 0.025, 0.5)
+    w.cmd = np.zeros((1, 1), orc.CMD_DTYPE)
+    w.cmd[0, 0]["wheel"] = (1.0, 0.0, 2.0, 0.0)
+    w.cmd[0, 0]["flags"] = orc.CMD_DRIVE
+    w.step(120)
+    vx, vy, wz = (float(w.vel[0, 0, k]) for k in (0, 1, 3))
+    assert wz == pytest.approx(2.0, abs=0.2)    # P-controlled wheels: steady-state lag while turning
+    assert np.hypot(vx, vy) == pytest.approx(1.0, abs=0.2)
+
+
+def test_sincos_accuracy(orc):
+    L = orc.lib()
+    s, c = C.c_float(), C.c_float()
+    worst = 0.0
+    for x in np.linspace(-7.0, 7.0, 2001, dtype=np.float32):
+        L.orc_sincos(C.c_float(float(x)), C.byref(s), C.byref(c))
+        worst = max(worst, abs(s.value - np.sin(np.float64(x))), abs(c.value - np.cos(np.float64(x))))
+    assert worst < 5e-7
+
+
+def test_determinism_and_world_independence(orc):
+    a = orc.Worlds(8, 12)
+    b = orc.Worlds(4, 12, world0=4)
+    for p in range(3):
+        a.gen_commands(p, 1); b.gen_commands(p, 1)
+        a.step(30, threads=3); b.step(30)
+    np.testing.assert_array_equal(a.pos[4:], b.pos)
+    np.testing.assert_array_equal(a.aux[4:], b.aux)
+
+
+def test_energy_does_not_grow_without_commands(orc):
+    w = orc.Worlds(16, 12)
+    def energy():
+        m = np.array([2.0] * 12 + [0.046])
+        return (0.5 * m * (w.vel[..., :3].astype(np.float64) ** 2).sum(-1) + m * 9.80665 * w.pos[..., 2]).sum(-1)
+    e0 = energy()
+    for _ in range(20):
+        w.step(10)
+        e1 = energy()
+        assert (e1 <= e0 + 1e-3).all()
+        e0 = e1
