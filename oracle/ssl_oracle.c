@@ -52,6 +52,7 @@ static const float WSIN[4] = {-0.8660254f, -0.70710677f, 0.70710677f, 0.8660254f
 static const float WCOS[4] = {0.5f, -0.70710677f, -0.70710677f, 0.5f};
 
 #define MAX_SERIAL_ROWS 64
+#define MAX_BODY_STATICS 4
 
 void orc_params_default(orc_params *p) {
   memset(p, 0, sizeof *p);
@@ -481,8 +482,10 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
     if (gen_ball_robot(&g, i, &r)) { if (nrows < cap) rows[nrows++] = r; else overflow = 1; }
   }
   for (int b = 0; b < N; b++) {
-    row_t tmp[11];
-    int c = gen_statics(&g, d, b, tmp, 11);
+    /* at most MAX_BODY_STATICS wall/goal rows per body, first ones in canonical order (STEP_SPEC 4.3) */
+    row_t tmp[MAX_BODY_STATICS];
+    int c = gen_statics(&g, d, b, tmp, MAX_BODY_STATICS);
+    if (c > MAX_BODY_STATICS) { overflow = 1; c = MAX_BODY_STATICS; }
     for (int k = 0; k < c; k++) { if (nrows < cap) rows[nrows++] = tmp[k]; else overflow = 1; }
   }
   int nground = 0;
