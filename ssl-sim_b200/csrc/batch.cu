@@ -32,6 +32,7 @@ void sslsim_derive_field(const FieldGeometry *f, DevField *d) {
   d->goal_back = d->half_len + f->goal_depth;
   d->goal_height = f->goal_height;
   d->goal_reach_y = f->goal_width / 2 + f->goal_wall_width;
+  d->goal_reach_x = f->field_length / 2 + f->goal_depth + f->goal_wall_width;
   const float ww = f->goal_wall_width, gd = f->goal_depth, gw = f->goal_width, gh = f->goal_height;
   const float sx = -d->half_len + (-gd / 2 - ww / 2), shx = gd / 2 + ww / 2;
   const float sy = gw / 2 + ww / 2, shy = ww / 2;
@@ -74,7 +75,7 @@ static void batch_free(WorldBatch *b) {
   for (World *w : b->views) delete w;
   cudaFree(b->d_pos); cudaFree(b->d_vel); cudaFree(b->d_aux); cudaFree(b->d_cmd);
   cudaFree(b->d_robot_ids); cudaFree(b->d_world_ids); cudaFree(b->d_gather); cudaFree(b->d_stats);
-  cudaFree(b->d_rep);
+  cudaFree(b->d_rep); cudaFree(b->d_field); cudaFree(b->d_prof);
   if (b->h_gather) cudaFreeHost(b->h_gather);
   for (cudaEvent_t e : b->kev) cudaEventDestroy(e);
   if (b->ev0) cudaEventDestroy(b->ev0);
@@ -121,7 +122,10 @@ WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_
             sslsim_check(b, cudaMalloc(&b->d_vel, nb * sizeof(float4)), "cudaMalloc(vel)") &&
             sslsim_check(b, cudaMalloc(&b->d_aux, (size_t)n_worlds * 8 * sizeof(uint32_t)), "cudaMalloc(aux)") &&
             sslsim_check(b, cudaMalloc(&b->d_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)") &&
-            sslsim_check(b, cudaMalloc(&b->d_robot_ids, SSLSIM_MAX_BODIES * sizeof(int)), "cudaMalloc(ids)");
+            sslsim_check(b, cudaMalloc(&b->d_robot_ids, SSLSIM_MAX_BODIES * sizeof(int)), "cudaMalloc(ids)") &&
+            sslsim_check(b, cudaMalloc(&b->d_field, sizeof(DevField)), "cudaMalloc(field)") &&
+            sslsim_check(b, cudaMemcpyAsync(b->d_field, &b->dfield, sizeof(DevField), cudaMemcpyHostToDevice, b->stream),
+                         "cudaMemcpy(field)");
   if (ok && n_robots > 0)
     ok = sslsim_check(b, cudaMemcpyAsync(b->d_robot_ids, b->robot_ids.data(), n_robots * sizeof(int),
                                          cudaMemcpyHostToDevice, b->stream), "cudaMemcpy(ids)");
@@ -140,7 +144,7 @@ int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float t
     StepArgs a;
     a.pos = b->d_pos; a.vel = b->d_vel; a.aux = b->d_aux; a.cmd = b->cmd_active;
     a.n_worlds = b->W; a.n_robots = b->R; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
-    a.f = b->dfield; a.p = b->params;
+    a.f = b->dfield; a.f_dev = b->d_field; a.p = b->params; a.prof = b->d_prof;
     if (b->ktiming) {
       if (b->kev_used + 2 > b->kev.size()) {
         for (int k = 0; k < 2; ++k) {
@@ -430,6 +434,21 @@ int world_batch_kernel_time(struct WorldBatch *b, float *total_ms, int *launches
   if (reset) b->kev_used = 0;
   return SSLSIM_OK;
 }
+
+#ifdef SSLSIM_PROFILE
+/* profile builds only (not part of the public ABI): per-world counters of the last step launch */
+int world_batch_profile_counters(struct WorldBatch *b, unsigned *out) {
+  ENTER(b);
+  if (!b->d_prof) {
+    CK(cudaMalloc(&b->d_prof, (size_t)b->W * 8 * sizeof(unsigned)));
+    CK(cudaMemset(b->d_prof, 0, (size_t)b->W * 8 * sizeof(unsigned)));
+    return 1;
+  }
+  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaMemcpy(out, b->d_prof, (size_t)b->W * 8 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  return SSLSIM_OK;
+}
+#endif
 
 int world_batch_set_lanes_per_world(struct WorldBatch *b, int lanes) {
   if (!b) return SSLSIM_E_ARG;

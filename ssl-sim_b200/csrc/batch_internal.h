@@ -23,6 +23,8 @@ struct WorldBatch {
   FieldGeometry field{};
   const FieldGeometry *field_ptr = nullptr; /* the caller's (borrowed) pointer, returned by world_get_field */
   DevField dfield{};
+  DevField *d_field = nullptr; /* device copy for the out-of-line general path */
+  unsigned *d_prof = nullptr;  /* SSLSIM_PROFILE builds only */
   SslSimParams params{};
   float4 *d_pos = nullptr, *d_vel = nullptr;
   uint32_t *d_aux = nullptr;

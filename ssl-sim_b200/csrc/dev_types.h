@@ -15,6 +15,7 @@ struct DevField {
   float half_len, half_wid, limit_x, limit_y;
   float goal_half_w, goal_back, goal_height;
   float goal_reach_y; /* goal_width/2 + goal_wall_width: |y| extent of the goal solids */
+  float goal_reach_x; /* field_length/2 + goal_depth + goal_wall_width: |x| extent of the goal solids */
   float lo[6][3], hi[6][3]; /* 6 goal boxes: -x goal {side -y, side +y, rear}, +x goal mirrored */
 };
 
@@ -25,8 +26,10 @@ struct StepArgs {
   const RobotCommand *cmd; /* [W][R] or NULL */
   int n_worlds, n_robots, n_steps, substeps;
   float h;
-  DevField f;
+  DevField f;            /* by value: constant bank */
+  const DevField *f_dev; /* the same in global memory, for the out-of-line general path */
   SslSimParams p;
+  unsigned *prof; /* SSLSIM_PROFILE builds: [W][8] per-world counters, else unused */
 };
 
 void sslsim_derive_field(const FieldGeometry *g, DevField *d);
