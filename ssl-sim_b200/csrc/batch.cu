@@ -92,6 +92,10 @@ WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_
             n_worlds, n_robots, SSLSIM_MAX_ROBOTS);
     return nullptr;
   }
+  if (!(field_limit_x(field) >= 0.5f) || !(field_limit_y(field) >= 0.5f)) {
+    fprintf(stderr, "sslsim_b200: new_world_batch: field walls closer than 0.5 m to the centre are not supported\n");
+    return nullptr;
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0) {
