@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--large-worlds", type=int, default=131072,
+                    help="extra measurement at this many worlds per GPU (0 = skip); not the headline value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -306,6 +308,35 @@ def main():
                "d2h_bytes_per_step": W * 32, "ms_per_step": float(te[0]) * 1e3 / K,
                "api": "world_batch_set_commands(host) + world_batch_step(30) + world_batch_read_aux(host)"}
 
+    # ---- extra: the per-GPU shard of configs[4] (1,048,576 worlds over 8 GPUs = 131,072 per GPU) ---------------
+    large = None
+    if args.large_worlds > 0:
+        WL, KL = args.large_worlds, 8
+        first_l, _ = sim.shard_range(WL * world_size, rank, world_size)
+        bl = sim.WorldBatch(WL, R, device=local_rank, seed=SEED, first_world_id=first_l)
+        bl.gen_commands(0, 0)
+        bl.step(SETTLE_STEPS)
+        for k in range(3):
+            bl.gen_commands(1 + k, 0)
+            bl.step(WORLD_STEPS_PER_STEP)
+        bl.sync()
+        bl.enable_kernel_timing(True)
+        bl.kernel_time(reset=True)
+        barrier()
+        for k in range(KL):
+            bl.gen_commands(4 + k, 0)          # 3 us generator launch, outside the event pair of the step
+            bl.step(WORLD_STEPS_PER_STEP)
+        ms_l, n_l = bl.kernel_time(reset=True)
+        tl = torch.tensor([ms_l], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        v_l = WL * world_size * WORLD_STEPS_PER_STEP * KL / (float(tl[0]) * 1e-3)
+        large = {"workload": "configs[4] shard: %d 6v6 worlds per GPU, same commands, %d timed launches "
+                             "(working set %.0f MiB > L2 at 131,072)" % (WL, KL, WL * (bpws - 16 + 32) / 2 ** 20),
+                 "value": v_l, "unit": "world-steps/s", "ms_per_launch": float(tl[0]) / KL,
+                 "roofline_frac": (bpws * WL * WORLD_STEPS_PER_STEP) / (float(tl[0]) / KL * 1e-3) / 1e9 / measured_peak()[0]}
+        bl.close()
+
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
@@ -343,6 +374,7 @@ def main():
                          "note": "latency/issue-bound fused kernel: state stays in registers for the 30 "
                                  "world-steps of a launch; see DESIGN.md"},
             "cpu_baseline": cpu,
+            "large_batch": large,
             "episode_stats": total_stats,
         }
         print(json.dumps(line), flush=True)
