@@ -129,6 +129,13 @@ BATCH_SYMBOLS = [
     ("world_batch_last_error", _I, [_VP]), ("world_batch_error_string", C.c_char_p, [_VP]),
     ("sslsim_b200_version", C.c_char_p, []),
 ]
+WIRE_SYMBOLS = [
+    ("serialize_world", _I, [_VP, _VP, _I]), ("serialize_field", _I, [C.POINTER(FieldGeometry), _VP, _I]),
+    ("sslsim_encode_detection", _I, [C.c_uint, C.c_double, C.c_double, _VP, _VP, _I, _VP, _I]),
+    ("world_batch_serialize_detections", _I, [_VP, _VP, _I, _VP, C.c_size_t, _VP]),
+    ("sslsim_decode_grsim_packet", _I, [_VP, C.c_size_t, _I, _VP, _VP, C.POINTER(_I), _VP, C.POINTER(_I),
+                                        C.POINTER(C.c_double)]),
+]
 DATA_SYMBOLS = ["FIELD_2014_SINGLE", "FIELD_2014_DOUBLE", "FIELD_2015", "FIELD_DIV_A"]
 
 _LIB = None
@@ -148,12 +155,44 @@ def lib():
             raise RuntimeError("sslsim_b200: %s is missing; build it with __graft_entry__.build() or "
                                "`make -C ssl-sim_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
-        for name, res, args in LEGACY_SYMBOLS + BATCH_SYMBOLS:
+        for name, res, args in LEGACY_SYMBOLS + BATCH_SYMBOLS + WIRE_SYMBOLS:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+def encode_detection(frame_number, t_capture, t_sent, record, teams):
+    rec = np.ascontiguousarray(record, np.float32)
+    tm = np.ascontiguousarray(teams, np.int32)
+    buf = np.empty(64 + 48 * (tm.size + 1), np.uint8)
+    n = lib().sslsim_encode_detection(frame_number, t_capture, t_sent, _ptr(rec), _ptr(tm), tm.size, _ptr(buf), buf.size)
+    if n < 0:
+        raise SslSimError("sslsim_encode_detection failed")
+    return buf[:n].tobytes()
+
+
+def serialize_field(fld):
+    buf = np.empty(256, np.uint8)
+    n = lib().serialize_field(C.byref(fld), _ptr(buf), buf.size)
+    if n < 0:
+        raise SslSimError("serialize_field failed")
+    return buf[:n].tobytes()
+
+
+def decode_grsim_packet(data, n_robots, cmds=None):
+    """-> (cmds [n_robots] CMD_DTYPE, robot replacements, ball replacement or None, timestamp, n decoded)."""
+    cmds = np.zeros(n_robots, CMD_DTYPE) if cmds is None else np.ascontiguousarray(cmds, CMD_DTYPE)
+    rr = np.zeros(max(n_robots, 1), ROBOT_REPLACEMENT_DTYPE)
+    br = np.zeros(1, BALL_REPLACEMENT_DTYPE)
+    nrr, hb, ts = C.c_int(rr.size), C.c_int(0), C.c_double(0.0)
+    raw = np.frombuffer(bytes(data), np.uint8)
+    n = lib().sslsim_decode_grsim_packet(_ptr(raw) if raw.size else None, raw.size, n_robots, _ptr(cmds), _ptr(rr),
+                                         C.byref(nrr), _ptr(br), C.byref(hb), C.byref(ts))
+    if n < 0:
+        raise SslSimError("malformed grSim packet")
+    return cmds, rr[:nrr.value], (br[0] if hb.value else None), ts.value, n
 
 
 def field(name="FIELD_2015"):
@@ -276,6 +315,16 @@ class WorldBatch:
         assert n == out.nbytes
         return out
 
+    def serialize_detections(self, world_ids):
+        """One SSL_WrapperPacket{detection} per observed world (bytes objects)."""
+        ids = np.ascontiguousarray(world_ids, np.int32)
+        out = np.empty(ids.size * (64 + 48 * (self.R + 1)), np.uint8)
+        sizes = np.zeros(ids.size, np.int32)
+        n = self._ck(lib().world_batch_serialize_detections(self._h, _ptr(ids), ids.size, _ptr(out), out.nbytes, _ptr(sizes)))
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        assert offs[-1] == n
+        return [out[offs[i]:offs[i + 1]].tobytes() for i in range(ids.size)]
+
     def reduce_stats(self):
         st = BatchStats()
         self._ck(lib().world_batch_reduce_stats(self._h, C.byref(st)))
@@ -391,6 +440,13 @@ class World:
     def robot_vel(self, i):
         p = lib().robot_get_vel(self.robot(i))
         return (p.x, p.y, p.w)
+
+    def serialize(self):
+        buf = np.empty(10240, np.uint8)     # BUFFER_SIZE of reference src/main.c:74
+        n = lib().serialize_world(self._h, _ptr(buf), buf.size)
+        if n < 0:
+            raise SslSimError("serialize_world failed")
+        return buf[:n].tobytes()
 
     def ball_vec(self):
         v = lib().ball_get_vec(self.ball())

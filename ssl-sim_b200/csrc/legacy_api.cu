@@ -36,7 +36,6 @@ float u01(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
 }
 
 WorldBatch *B(const World *w) { return w->batch; }
-int nbodies(const World *w) { return w->n_robots + 1; }
 
 /* device -> host mirror of this world's slice */
 bool pull(World *w) {

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include "sslsim.h"
 #include "sslsim_batch.h"
+#include "serialize.h"
 
 int main(int argc, char **argv) {
   int steps = argc > 1 ? atoi(argv[1]) : 60;
@@ -31,6 +32,13 @@ int main(int argc, char **argv) {
     const struct Robot *r = world_get_robot(world, i);
     struct Pos2 p = robot_get_pos(r);
     printf("robot %d %d %.9g %.9g %.9g\n", get_id(r), (int)get_team(r), (double)p.x, (double)p.y, (double)p.w);
+  }
+  {
+    /* the packet path of the reference loop (src/main.c:83-91) */
+    char buffer[10240];
+    int n = serialize_world(world, buffer, (int)sizeof buffer);
+    int g = serialize_field(world_get_field(world), buffer, (int)sizeof buffer);
+    printf("packets %d %d\n", n, g);
   }
   delete_world(world);
   return 0;

@@ -32,11 +32,12 @@ def _declared_functions(path):
 
 def test_every_declared_symbol_is_exported(sim):
     L = sim.lib()
-    declared = _declared_functions(os.path.join(INC, "sslsim.h")) + _declared_functions(os.path.join(INC, "sslsim_batch.h"))
-    assert len(declared) >= 37 + 30
+    declared = (_declared_functions(os.path.join(INC, "sslsim.h")) + _declared_functions(os.path.join(INC, "sslsim_batch.h")) +
+                _declared_functions(os.path.join(INC, "serialize.h")))
+    assert len(declared) >= 37 + 30 + 5
     missing = [n for n in declared if not hasattr(L, n)]
     assert not missing, missing
-    bound = {n for n, _, _ in sim.LEGACY_SYMBOLS + sim.BATCH_SYMBOLS}
+    bound = {n for n, _, _ in sim.LEGACY_SYMBOLS + sim.BATCH_SYMBOLS + sim.WIRE_SYMBOLS}
     assert set(declared) <= bound, set(declared) - bound      # the Python mirror binds all of them
     for d in sim.DATA_SYMBOLS:
         sim.FieldGeometry.in_dll(L, d)
@@ -89,7 +90,7 @@ def test_c_client_compiles_and_links(sim, tmp_path):
     subprocess.run(cmd, check=True)
     assert exe.exists()
     # the per-topic forwarding headers compile stand-alone as C and as C++
-    for h in ("world.h", "robot.h", "ball.h", "team.h", "vector.h", "field.h", "sslsim.h", "sslsim_batch.h"):
+    for h in ("world.h", "robot.h", "ball.h", "team.h", "vector.h", "field.h", "sslsim.h", "sslsim_batch.h", "serialize.h"):
         for comp, std in (("gcc", "-std=c11"), ("g++", "-std=c++11")):
             subprocess.run([comp, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", INC,
                             "-x", "c" if comp == "gcc" else "c++", os.path.join(INC, h)], check=True)

@@ -375,3 +375,27 @@ def test_c_client_runs_like_reference_cli(sim, orc, tmp_path):
         f = out[2 + i].split()
         assert (int(f[1]), int(f[2])) == (i // 2, i % 2)
         assert [np.float32(v) for v in f[3:]] == list(o.pos[0, i, [0, 1, 3]])
+    sizes = [int(v) for v in out[14].split()[1:]]
+    assert 440 < sizes[0] < 500 and 20 < sizes[1] < 60      # detection ~475 B, geometry packet
+
+
+def test_serialize_world_and_batch(sim, orc):
+    """serialize_world (reference src/serialize.cpp:17-76) on a device world and the batched packet path, decoded
+    with python-protobuf and compared with the oracle state."""
+    import ssl_protos
+    pb = ssl_protos.build()
+    W, R = 6, 12
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    b.step(75); o.step(75)
+    pk = b.serialize_detections([5, 0])
+    for data, w in zip(pk, (5, 0)):
+        d = pb["SSL_WrapperPacket"].FromString(data).detection
+        assert d.frame_number == 75 and d.camera_id == 0 and d.t_capture == b.timestamp
+        assert (np.float32(d.balls[0].x), np.float32(d.balls[0].y), np.float32(d.balls[0].z)) == tuple(o.pos[w, R, :3])
+        assert len(d.robots_blue) == 6 and len(d.robots_yellow) == 6
+        for k, m in enumerate(d.robots_yellow):
+            assert m.robot_id == k and (np.float32(m.x), np.float32(m.orientation)) == (o.pos[w, 2 * k + 1, 0], o.pos[w, 2 * k + 1, 3])
+    v = b.get_world(3)
+    d = pb["SSL_WrapperPacket"].FromString(v.serialize()).detection
+    assert d.frame_number == 75 and np.float32(d.robots_blue[2].y) == o.pos[3, 4, 1] and d.t_sent > 1.5e9
