@@ -167,6 +167,16 @@ size_t world_batch_detection_record_size(const struct WorldBatch *batch);
  * every sslsim.h call (host-mirrored; getters synchronise).  Owned by the batch. */
 struct World *world_batch_get_world(struct WorldBatch *batch, int index);
 
+/* ---- snapshot / fork: what reference clone_world (src/world.h:22, src/sslsim.cpp:254-273,
+ * which never re-adds the bodies upstream) is for -- AI look-ahead (README goal 2) -- done batched and on the
+ * device.  The state is flat POD, so a snapshot is three device-to-device copies. */
+struct WorldSnapshot;
+struct WorldSnapshot *world_batch_snapshot(struct WorldBatch *batch);           /* NULL on failure */
+int world_batch_restore(struct WorldBatch *batch, const struct WorldSnapshot *snap); /* same shape required */
+void world_snapshot_free(struct WorldSnapshot *snap);
+/* copy the state (pose, velocity, aux words) of world `src` into the n worlds `dst[]` of the same batch */
+int world_batch_fork(struct WorldBatch *batch, int src, const int *dst, int n);
+
 /* ---- episode statistics (K4): per-batch reduction on the device. */
 int world_batch_reduce_stats(struct WorldBatch *batch, struct BatchStats *out);
 

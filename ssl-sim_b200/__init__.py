@@ -121,6 +121,8 @@ BATCH_SYMBOLS = [
     ("world_batch_detection_record_size", C.c_size_t, [_VP]),
     ("world_batch_get_world", _VP, [_VP, _I]),
     ("world_batch_reduce_stats", _I, [_VP, C.POINTER(BatchStats)]),
+    ("world_batch_snapshot", _VP, [_VP]), ("world_batch_restore", _I, [_VP, _VP]), ("world_snapshot_free", None, [_VP]),
+    ("world_batch_fork", _I, [_VP, _I, _VP, _I]),
     ("world_batch_stream", _VP, [_VP]), ("world_batch_set_stream", _I, [_VP, _VP]),
     ("world_batch_timer_start", _I, [_VP]), ("world_batch_timer_stop", _I, [_VP, C.POINTER(_F)]),
     ("world_batch_enable_kernel_timing", _I, [_VP, _I]),
@@ -324,6 +326,22 @@ class WorldBatch:
         offs = np.concatenate([[0], np.cumsum(sizes)])
         assert offs[-1] == n
         return [out[offs[i]:offs[i + 1]].tobytes() for i in range(ids.size)]
+
+    def snapshot(self):
+        h = lib().world_batch_snapshot(self._h)
+        if not h:
+            raise SslSimError("world_batch_snapshot failed")
+        return h
+
+    def restore(self, snap):
+        self._ck(lib().world_batch_restore(self._h, snap))
+
+    def free_snapshot(self, snap):
+        lib().world_snapshot_free(snap)
+
+    def fork(self, src, dst):
+        dst = np.ascontiguousarray(dst, np.int32)
+        self._ck(lib().world_batch_fork(self._h, src, _ptr(dst), dst.size))
 
     def reduce_stats(self):
         st = BatchStats()

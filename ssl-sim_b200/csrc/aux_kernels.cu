@@ -144,6 +144,20 @@ __global__ void gather_detections(const float4 *pos, int W, int R, const int *wo
   }
 }
 
+/* fork: one warp per destination world copies the source world's bodies and aux words */
+__global__ void fork_worlds(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, int src, const int *dst, int n) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const int d = dst[warp];
+  if (d < 0 || d >= W || d == src) return;
+  const int N = R + 1;
+  for (int b = lane; b < N; b += 32) {
+    pos[(size_t)d * N + b] = pos[(size_t)src * N + b];
+    vel[(size_t)d * N + b] = vel[(size_t)src * N + b];
+  }
+  if (lane < 8) aux[(size_t)d * 8 + lane] = aux[(size_t)src * 8 + lane];
+}
+
 /* K4: grid-stride block reduction of the aux words into 8 u64 (atomics on the final add) */
 __global__ void reduce_stats(const float4 *pos, const float4 *vel, const uint32_t *aux, int W, int R,
                              uint64_t world0, unsigned long long *out8) {
@@ -219,6 +233,13 @@ cudaError_t sslsim_launch_gather(const float4 *pos, int W, int R, const int *wor
                                  const int *robot_ids, float *out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   gather_detections<<<(n + 3) / 4, 128, 0, s>>>(pos, W, R, world_ids, n, robot_ids, out);
+  return cudaGetLastError();
+}
+
+cudaError_t sslsim_launch_fork(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, int src, const int *dst, int n,
+                               cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  fork_worlds<<<(n + 3) / 4, 128, 0, s>>>(pos, vel, aux, W, R, src, dst, n);
   return cudaGetLastError();
 }
 

@@ -379,6 +379,64 @@ int world_batch_gather_detections(struct WorldBatch *b, const int *world_ids, in
   return (int)((size_t)n * rec);
 }
 
+struct WorldSnapshot {
+  int device, W, R;
+  float4 *pos, *vel;
+  uint32_t *aux;
+  unsigned int frame;
+  float timestamp;
+};
+
+struct WorldSnapshot *world_batch_snapshot(struct WorldBatch *b) {
+  if (!b || b->last_error == SSLSIM_E_CUDA) return nullptr;
+  cudaSetDevice(b->device);
+  WorldSnapshot *s = new (std::nothrow) WorldSnapshot();
+  if (!s) return nullptr;
+  s->device = b->device; s->W = b->W; s->R = b->R; s->frame = b->frame; s->timestamp = b->timestamp;
+  s->pos = s->vel = nullptr; s->aux = nullptr;
+  const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4), na = (size_t)b->W * 8 * sizeof(uint32_t);
+  const bool ok = sslsim_check(b, cudaMalloc(&s->pos, nb), "snapshot alloc") && sslsim_check(b, cudaMalloc(&s->vel, nb), "snapshot alloc") &&
+                  sslsim_check(b, cudaMalloc(&s->aux, na), "snapshot alloc") &&
+                  sslsim_check(b, cudaMemcpyAsync(s->pos, b->d_pos, nb, cudaMemcpyDeviceToDevice, b->stream), "snapshot copy") &&
+                  sslsim_check(b, cudaMemcpyAsync(s->vel, b->d_vel, nb, cudaMemcpyDeviceToDevice, b->stream), "snapshot copy") &&
+                  sslsim_check(b, cudaMemcpyAsync(s->aux, b->d_aux, na, cudaMemcpyDeviceToDevice, b->stream), "snapshot copy") &&
+                  sslsim_check(b, cudaStreamSynchronize(b->stream), "snapshot sync");
+  if (!ok) { world_snapshot_free(s); return nullptr; }
+  return s;
+}
+
+int world_batch_restore(struct WorldBatch *b, const struct WorldSnapshot *s) {
+  ENTER(b);
+  if (!s || s->W != b->W || s->R != b->R || s->device != b->device) return SSLSIM_E_ARG;
+  const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4), na = (size_t)b->W * 8 * sizeof(uint32_t);
+  CK(cudaMemcpyAsync(b->d_pos, s->pos, nb, cudaMemcpyDeviceToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_vel, s->vel, nb, cudaMemcpyDeviceToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_aux, s->aux, na, cudaMemcpyDeviceToDevice, b->stream));
+  b->frame = s->frame; b->timestamp = s->timestamp;
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+void world_snapshot_free(struct WorldSnapshot *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->pos); cudaFree(s->vel); cudaFree(s->aux);
+  delete s;
+}
+
+int world_batch_fork(struct WorldBatch *b, int src, const int *dst, int n) {
+  ENTER(b);
+  if (src < 0 || src >= b->W || n < 0 || (n > 0 && !dst)) return SSLSIM_E_ARG;
+  if (n == 0) return SSLSIM_OK;
+  int rc = ensure_rep(b, (size_t)n * sizeof(int));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(b->d_rep, dst, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  CK(sslsim_launch_fork(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, src, (const int *)b->d_rep, n, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
 int world_batch_reduce_stats(struct WorldBatch *b, struct BatchStats *out) {
   ENTER(b);
   if (!out) return SSLSIM_E_ARG;

@@ -399,3 +399,42 @@ def test_serialize_world_and_batch(sim, orc):
     v = b.get_world(3)
     d = pb["SSL_WrapperPacket"].FromString(v.serialize()).detection
     assert d.frame_number == 75 and np.float32(d.robots_blue[2].y) == o.pos[3, 4, 1] and d.t_sent > 1.5e9
+
+
+def test_snapshot_restore_and_fork(sim, orc):
+    """Batched snapshot / fork (clone_world done right, SURVEY 8f rank 3): restoring replays bit-identically;
+    forked worlds evolve exactly like their source under the same commands."""
+    W, R = 16, 12
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    b.gen_commands(0, 1); o.gen_commands(0, 1)
+    b.step(100); o.step(100)
+    snap = b.snapshot()
+    f0, t0 = b.frame_number, b.timestamp
+    b.gen_commands(1, 1); b.step(50)
+    first = b.read_state()
+    b.restore(snap)
+    assert (b.frame_number, b.timestamp) == (f0, t0)
+    b.gen_commands(1, 1); b.step(50)
+    again = b.read_state()
+    for k in range(3):
+        np.testing.assert_array_equal(first[k], again[k])
+    o.gen_commands(1, 1); o.step(50)
+    _compare(again, o, 50)
+    b.free_snapshot(snap)
+    # fork world 3 into worlds 5, 9, 10 and give all four the same commands
+    b.fork(3, [5, 9, 10])
+    o.gen_commands(2, 1)
+    cmd = o.cmd.copy()
+    for d in (5, 9, 10):
+        cmd[d] = cmd[3]
+    b.set_commands(cmd)
+    b.step(60)
+    pos, vel, aux = b.read_state()
+    for d in (5, 9, 10):
+        np.testing.assert_array_equal(pos[d], pos[3]); np.testing.assert_array_equal(vel[d], vel[3]); np.testing.assert_array_equal(aux[d], aux[3])
+    o.cmd = cmd
+    for d in (5, 9, 10):
+        o.pos[d], o.vel[d], o.aux[d] = o.pos[3], o.vel[3], o.aux[3]
+    o.step(60)
+    _compare((pos, vel, aux), o, 60)
