@@ -352,12 +352,21 @@ def main():
         per_launch_bytes = bpws * W * WORLD_STEPS_PER_STEP
         per_launch_s = kern_ms_max * 1e-3 / K
         achieved = per_launch_bytes / per_launch_s / 1e9
-        traffic = None
+        traffic, issue = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 with open(tp) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
+                    tj = json.load(f)
+                traffic = tj.get("dram_bytes_per_launch")
+                # secondary ceiling: the kernel is issue/latency-bound, so also report warp-instructions issued per
+                # second against 148 SMs x 4 schedulers x SM clock (instruction count per world-step from the
+                # committed ncu capture of the 4096-world launch)
+                ipw = tj["warp_instructions_per_launch"] / (4096 * WORLD_STEPS_PER_STEP)
+                peak_issue = 148 * 4 * (clocks.get("sm_max_mhz") or 1965) * 1e6
+                issue = {"warp_instructions_per_world_step": ipw, "achieved_per_s": ipw * value / world_size,
+                         "peak_per_s": peak_issue, "frac": ipw * value / world_size / peak_issue,
+                         "source": "profiles/traffic.json (ncu smsp__inst_executed.sum)"}
             except Exception:
                 traffic = None
         line = {
@@ -370,7 +379,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "step_worlds", "algorithmic_bytes_per_launch": per_launch_bytes,
-                         "bytes_per_world_step": bpws, "kernel_ms_per_launch": kern_ms_max / K,
+                         "bytes_per_world_step": bpws, "kernel_ms_per_launch": kern_ms_max / K, "issue_ceiling": issue,
                          "note": "latency/issue-bound fused kernel: state stays in registers for the 30 "
                                  "world-steps of a launch; see DESIGN.md"},
             "cpu_baseline": cpu,

@@ -52,7 +52,10 @@ def tobytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 tr = sum(tobytes(r[ir], units[ir]) + tobytes(r[iw], units[iw]) for r in data) / len(data)
-json.dump({"dram_bytes_per_launch": tr, "kernel": "step_worlds", "source": os.path.basename(rep),
+ii = hdr.index("smsp__inst_executed.sum")
+inst = sum(float(r[ii].replace(",", "")) for r in data) / len(data)
+json.dump({"dram_bytes_per_launch": tr, "warp_instructions_per_launch": inst,
+           "launch_shape": "4096 6v6 worlds x 30 world-steps", "kernel": "step_worlds", "source": os.path.basename(rep),
            "how": "dram__bytes_read.sum + dram__bytes_write.sum, mean over %d captured launches, ncu --set full" % len(data)},
           open(os.path.join(out, "traffic.json"), "w"), indent=1)
 
