@@ -79,7 +79,7 @@ enum {
                              bit17 non-finite state (sticky) */
   SSLSIM_AUX_PEAK2 = 1,   /* f32 bits: peak |v_ball|^2 since the last kick */
   SSLSIM_AUX_TOUCH = 2,   /* robots that touched the ball during the last step (bit i = robot i) */
-  SSLSIM_AUX_RSVD = 3,
+  SSLSIM_AUX_RESTARTS = 3, /* restarts placed by world_batch_referee */
   SSLSIM_AUX_GOALS = 4,   /* goals_blue | goals_yellow << 16 */
   SSLSIM_AUX_OUTS = 5,    /* ball-out count | kicks << 16 */
   SSLSIM_AUX_TOUCHES = 6, /* sum over steps of popcount(touch mask) */
@@ -166,6 +166,12 @@ size_t world_batch_detection_record_size(const struct WorldBatch *batch);
 /* ---- legacy view: member i of the batch as a `struct World *` usable with
  * every sslsim.h call (host-mirrored; getters synchronise).  Owned by the batch. */
 struct World *world_batch_get_world(struct WorldBatch *batch, int index);
+
+/* ---- referee restart placement (README goal 4, no upstream implementation).  For every world
+ * whose last step raised a goal event the ball is put on the centre spot; after ball-out it is put back 0.1 m
+ * inside the line it crossed; at rest on the ground.  The in-goal/out edge state is cleared and
+ * aux[SSLSIM_AUX_RESTARTS] counts.  Asynchronous on the batch stream. */
+int world_batch_referee(struct WorldBatch *batch);
 
 /* ---- snapshot / fork: what reference clone_world (src/world.h:22, src/sslsim.cpp:254-273,
  * which never re-adds the bodies upstream) is for -- AI look-ahead (README goal 2) -- done batched and on the

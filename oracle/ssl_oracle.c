@@ -667,6 +667,25 @@ void orc_step(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *p
   }
 }
 
+/* ---- referee restart placement (STEP_SPEC 7) ------------------------------------ */
+int orc_referee(const orc_field *f, int R, orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux) {
+  const uint32_t st = aux[ORC_AUX_STATUS];
+  const int goal = (st >> 12) & 3, out = (st >> 14) & 1;
+  if (!goal && !out) return 0;
+  const int B = R;
+  float x = 0.0f, y = 0.0f;
+  if (!goal) {
+    const float lx = f->field_length / 2 - 0.1f, ly = f->field_width / 2 - 0.1f;
+    x = clampf(pos[B].x, -lx, lx);
+    y = clampf(pos[B].y, -ly, ly);
+  }
+  pos[B].x = x; pos[B].y = y; pos[B].z = BALL_R; pos[B].w = 0.0f;
+  vel[B].x = 0.0f; vel[B].y = 0.0f; vel[B].z = 0.0f; vel[B].w = 0.0f;
+  aux[ORC_AUX_STATUS] = st & ~(7u << 8); /* not in a goal, not out: the next crossing is a new edge */
+  aux[ORC_AUX_RESTARTS] += 1u;
+  return 1;
+}
+
 /* ---- init / commands / gather ---------------------------------------------- */
 void orc_init_world(const orc_field *f, int R, uint64_t seed, uint64_t world_id, int mode,
                     orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux) {

@@ -70,7 +70,7 @@ enum {
                          bit16 row overflow (sticky); bit17 non-finite state (sticky) */
   ORC_AUX_PEAK2 = 1,  /* f32 bits: peak |v_ball|^2 since last kick */
   ORC_AUX_TOUCH = 2,  /* robots that touched the ball during the last step (bit i = robot i) */
-  ORC_AUX_RSVD = 3,
+  ORC_AUX_RESTARTS = 3, /* restarts placed by orc_referee */
   ORC_AUX_GOALS = 4,  /* goals_blue | goals_yellow << 16 */
   ORC_AUX_OUTS = 5,   /* ball_out count | kicks << 16 */
   ORC_AUX_TOUCHES = 6, /* sum over steps of popcount(touch mask) */
@@ -102,6 +102,12 @@ void orc_gen_commands(int n_robots, uint64_t seed, uint64_t world_id,
  * 6 floats per ball {conf,x,y,z,px,py} then 7 per robot {conf,id,x,y,yaw,px,py}
  * in world robot order.  ids: robot ids. Returns number of floats. */
 int orc_gather(int n_robots, const orc_vec4 *pos, const int *ids, float *out);
+
+/* referee restart placement (STEP_SPEC 7, builder-defined): if the last step raised a goal event the ball goes to
+ * the centre spot, if it raised ball-out the ball goes back 0.1 m inside the line it crossed; placed at rest
+ * on the ground (z = ball radius, zero velocity and spin), in-goal/out edge state cleared, aux[3]++.
+ * Returns 1 if the ball was re-placed. */
+int orc_referee(const orc_field *f, int n_robots, orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux);
 
 /* splitmix64-keyed uniform in [0,1) with 24 bits */
 float orc_u01(uint64_t seed, uint64_t a, uint64_t b, uint64_t c);

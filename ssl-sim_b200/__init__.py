@@ -24,7 +24,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 TEAM_NONE, TEAM_BLUE, TEAM_YELLOW = -1, 0, 1
 CMD_DRIVE, CMD_WHEELS, CMD_SPINNER = 1, 2, 4
 F_BALL_SPIN = 1
-AUX_STATUS, AUX_PEAK2, AUX_TOUCH, AUX_RSVD, AUX_GOALS, AUX_OUTS, AUX_TOUCHES, AUX_CONTACTS = range(8)
+AUX_STATUS, AUX_PEAK2, AUX_TOUCH, AUX_RESTARTS, AUX_GOALS, AUX_OUTS, AUX_TOUCHES, AUX_CONTACTS = range(8)
 MAX_ROBOTS = 31
 
 CMD_DTYPE = np.dtype([("wheel", np.float32, 4), ("kickspeedx", np.float32), ("kickspeedz", np.float32),
@@ -122,7 +122,7 @@ BATCH_SYMBOLS = [
     ("world_batch_get_world", _VP, [_VP, _I]),
     ("world_batch_reduce_stats", _I, [_VP, C.POINTER(BatchStats)]),
     ("world_batch_snapshot", _VP, [_VP]), ("world_batch_restore", _I, [_VP, _VP]), ("world_snapshot_free", None, [_VP]),
-    ("world_batch_fork", _I, [_VP, _I, _VP, _I]),
+    ("world_batch_fork", _I, [_VP, _I, _VP, _I]), ("world_batch_referee", _I, [_VP]),
     ("world_batch_stream", _VP, [_VP]), ("world_batch_set_stream", _I, [_VP, _VP]),
     ("world_batch_timer_start", _I, [_VP]), ("world_batch_timer_stop", _I, [_VP, C.POINTER(_F)]),
     ("world_batch_enable_kernel_timing", _I, [_VP, _I]),
@@ -326,6 +326,9 @@ class WorldBatch:
         offs = np.concatenate([[0], np.cumsum(sizes)])
         assert offs[-1] == n
         return [out[offs[i]:offs[i + 1]].tobytes() for i in range(ids.size)]
+
+    def referee(self):
+        self._ck(lib().world_batch_referee(self._h))
 
     def snapshot(self):
         h = lib().world_batch_snapshot(self._h)

@@ -144,6 +144,29 @@ __global__ void gather_detections(const float4 *pos, int W, int R, const int *wo
   }
 }
 
+/* referee restart placement (STEP_SPEC 7): one thread per world */
+__global__ void referee_restart(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, float field_length,
+                                float field_width) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  uint32_t *a = aux + (size_t)w * 8;
+  const uint32_t st = a[SSLSIM_AUX_STATUS];
+  const bool goal = ((st >> 12) & 3u) != 0, out = ((st >> 14) & 1u) != 0;
+  if (!goal && !out) return;
+  const size_t i = (size_t)w * (R + 1) + R;
+  float x = 0.0f, y = 0.0f;
+  if (!goal) {
+    const float lx = field_length / 2 - 0.1f, ly = field_width / 2 - 0.1f;
+    const float4 p = pos[i];
+    x = p.x < -lx ? -lx : (p.x > lx ? lx : p.x);
+    y = p.y < -ly ? -ly : (p.y > ly ? ly : p.y);
+  }
+  pos[i] = make_float4(x, y, BALL_R, 0.0f);
+  vel[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  a[SSLSIM_AUX_STATUS] = st & ~(7u << 8);
+  a[SSLSIM_AUX_RESTARTS] += 1u;
+}
+
 /* fork: one warp per destination world copies the source world's bodies and aux words */
 __global__ void fork_worlds(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, int src, const int *dst, int n) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -233,6 +256,13 @@ cudaError_t sslsim_launch_gather(const float4 *pos, int W, int R, const int *wor
                                  const int *robot_ids, float *out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   gather_detections<<<(n + 3) / 4, 128, 0, s>>>(pos, W, R, world_ids, n, robot_ids, out);
+  return cudaGetLastError();
+}
+
+cudaError_t sslsim_launch_referee(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, float field_length,
+                                  float field_width, cudaStream_t s) {
+  if (W <= 0) return cudaSuccess;
+  referee_restart<<<(W + 255) / 256, 256, 0, s>>>(pos, vel, aux, W, R, field_length, field_width);
   return cudaGetLastError();
 }
 

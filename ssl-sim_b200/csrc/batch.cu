@@ -379,6 +379,13 @@ int world_batch_gather_detections(struct WorldBatch *b, const int *world_ids, in
   return (int)((size_t)n * rec);
 }
 
+int world_batch_referee(struct WorldBatch *b) {
+  ENTER(b);
+  CK(sslsim_launch_referee(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->field.field_length, b->field.field_width, b->stream));
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
 struct WorldSnapshot {
   int device, W, R;
   float4 *pos, *vel;

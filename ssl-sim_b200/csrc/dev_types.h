@@ -46,6 +46,8 @@ cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, int n_worlds, 
                                         const BallReplacement *recs, int n, cudaStream_t s);
 cudaError_t sslsim_launch_gather(const float4 *pos, int n_worlds, int n_robots, const int *world_ids, int n,
                                  const int *robot_ids, float *out, cudaStream_t s);
+cudaError_t sslsim_launch_referee(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots,
+                                  float field_length, float field_width, cudaStream_t s);
 cudaError_t sslsim_launch_fork(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots, int src,
                                const int *dst, int n, cudaStream_t s);
 cudaError_t sslsim_launch_reduce(const float4 *pos, const float4 *vel, const uint32_t *aux, int n_worlds,

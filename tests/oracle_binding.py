@@ -61,6 +61,8 @@ def lib():
         L.orc_gen_commands.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, fp]
         L.orc_gather.argtypes = [C.c_int, fp, fp, fp]
         L.orc_gather.restype = C.c_int
+        L.orc_referee.argtypes = [C.POINTER(Field), C.c_int, fp, fp, fp]
+        L.orc_referee.restype = C.c_int
         L.orc_u01.argtypes = [C.c_uint64] * 4
         L.orc_u01.restype = C.c_float
         L.orc_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -114,6 +116,11 @@ class Worlds:
         lib().orc_step_many(C.byref(self.field), C.byref(self.params), self.R, self.W, _ptr(self.pos),
                             _ptr(self.vel), _ptr(self.aux), _ptr(self.cmd), n_steps, substeps,
                             C.c_float(float(h)), threads)
+
+    def referee(self):
+        L = lib()
+        return sum(L.orc_referee(C.byref(self.field), self.R, _ptr(self.pos[w]), _ptr(self.vel[w]), _ptr(self.aux[w]))
+                   for w in range(self.W))
 
     def gather(self, w, ids):
         out = np.zeros(6 + 7 * self.R, np.float32)

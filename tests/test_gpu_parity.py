@@ -473,3 +473,33 @@ def test_randomized_crowded_stress(sim, orc, R, lanes):
         o.step(10)
         _compare(b.read_state(), o, 10, "R=%d period %d" % (R, period))
     assert ((o.aux[:, 0] >> 16) & 1).mean() < 0.9     # most worlds are not in overflow, i.e. really compared
+
+
+def test_referee_restart_placement(sim, orc):
+    """Goal -> centre spot, ball-out -> 0.1 m inside the line; played for 6 s with the referee called every step
+    on both sides."""
+    W, R = 64, 12
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    pos, vel, aux = b.read_state()
+    rng = np.random.default_rng(11)
+    pos[:, :, 2] = 0.025
+    pos[:, R, 2] = 0.0215
+    pos[:, R, 0] = rng.uniform(-3, 3, W)
+    pos[:, R, 1] = rng.uniform(-0.4, 0.4, W)
+    ang = rng.uniform(-0.5, 0.5, W) + np.where(np.arange(W) % 2, np.pi, 0.0)
+    vel[:, R, 0] = 6.0 * np.cos(ang)
+    vel[:, R, 1] = 6.0 * np.sin(ang)
+    b.write_state(pos, vel, aux)
+    o.pos[...] = pos
+    o.vel[...] = vel
+    placed = 0
+    for step in range(360):
+        o.gen_commands(step // 30, 1)
+        if step % 30 == 0:
+            b.set_commands(o.cmd)
+        b.step(1); o.step(1)
+        b.referee(); placed += o.referee()
+    _compare(b.read_state(), o, 360)
+    assert placed > W // 2 and int(o.aux[:, 3].sum()) == placed
+    assert (np.abs(o.pos[:, R, 0]) <= 4.5 + 0.2).all()
