@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--periods-per-launch", type=int, default=10,
+                    help="device-resident arm: command periods (bench steps) fused into one step_worlds launch")
     ap.add_argument("--large-worlds", type=int, default=131072,
                     help="extra measurement at this many worlds per GPU (0 = skip); not the headline value")
     args = ap.parse_args()
@@ -251,29 +253,46 @@ def main():
         flush.zero_()
     allgather_stats()  # warms the NCCL communicator up
     torch.cuda.synchronize()
-    b.enable_kernel_timing(True)
-    b.kernel_time(reset=True)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    t_wall0 = time.perf_counter()
-    for k in range(K):
-        b.set_commands_device(stage.data_ptr() + (WU + k) * cmd_bytes)
-        b.step(WORLD_STEPS_PER_STEP)   # events bracket this launch on the batch's stream
-        b.sync()
-        flush.zero_()                   # L2 flush, outside the event pair
-        torch.cuda.synchronize()
-    total_stats = allgather_stats()
-    barrier()
-    wall_s = time.perf_counter() - t_wall0
-    clocks = sampler.finish()
-    kern_ms, launches = b.kernel_time(reset=True)
-    b.enable_kernel_timing(False)
-    assert launches == K
-    t = torch.tensor([kern_ms, wall_s * 1e3], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    kern_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    def device_arm(periods_per_launch, sample_clocks):
+        """K bench steps, `periods_per_launch` of them per step_worlds launch (the staged command blocks are
+        consecutive in HBM); CUDA events bracket every launch on the batch's stream, L2 flushed in between."""
+        b.enable_kernel_timing(True)
+        b.kernel_time(reset=True)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        t0 = time.perf_counter()
+        k = 0
+        while k < K:
+            p = min(periods_per_launch, K - k)
+            b.step_sequence_device(stage.data_ptr() + (WU + k) * cmd_bytes, p, WORLD_STEPS_PER_STEP)
+            b.sync()
+            flush.zero_()                   # L2 flush, outside the event pair
+            torch.cuda.synchronize()
+            k += p
+        stats = allgather_stats()
+        barrier()
+        wall = time.perf_counter() - t0
+        clk = sampler.finish() if sampler else None
+        ms, n = b.kernel_time(reset=True)
+        b.enable_kernel_timing(False)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), n, clk, stats
+
+    PPL = max(1, args.periods_per_launch)
+    snap = b.snapshot()
+    kern_ms_max, wall_ms_max, launches, clocks, total_stats = device_arm(PPL, True)
+    single = None
+    if PPL > 1:     # the same K steps again, one launch per command period (what a closed-loop caller does)
+        b.restore(snap)
+        ms1, _, n1, _, stats1 = device_arm(1, False)
+        assert stats1 == total_stats, "fused and per-period launches must produce identical worlds"
+        single = {"value": W * world_size * WORLD_STEPS_PER_STEP * K / (ms1 * 1e-3), "ms_per_step": ms1 / K,
+                  "launches": n1}
+    b.free_snapshot(snap)
     units = W * world_size * WORLD_STEPS_PER_STEP * K
     value = units / (kern_ms_max * 1e-3)
 
@@ -349,8 +368,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        per_launch_bytes = bpws * W * WORLD_STEPS_PER_STEP
-        per_launch_s = kern_ms_max * 1e-3 / K
+        per_launch_bytes = bpws * W * WORLD_STEPS_PER_STEP * K / launches
+        per_launch_s = kern_ms_max * 1e-3 / launches
         achieved = per_launch_bytes / per_launch_s / 1e9
         traffic, issue = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -375,11 +394,12 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, world_size),
             "wall_ms_per_step_incl_l2_flush": wall_ms_max / K,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": K + 1,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches + 1,
+            "periods_per_launch": PPL, "one_launch_per_period": single,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "step_worlds", "algorithmic_bytes_per_launch": per_launch_bytes,
-                         "bytes_per_world_step": bpws, "kernel_ms_per_launch": kern_ms_max / K, "issue_ceiling": issue,
+                         "bytes_per_world_step": bpws, "kernel_ms_per_launch": kern_ms_max / launches, "issue_ceiling": issue,
                          "note": "latency/issue-bound fused kernel: state stays in registers for the 30 "
                                  "world-steps of a launch; see DESIGN.md"},
             "cpu_baseline": cpu,

@@ -124,6 +124,15 @@ double world_batch_timestamp(const struct WorldBatch *batch);          /* src/ss
  * of 1/120 s). */
 int world_batch_step(struct WorldBatch *batch, int n_steps);
 int world_batch_step_delta(struct WorldBatch *batch, int n_steps, int substeps, float fixed_time_step);
+/* A command sequence in one launch: n_periods blocks of [n_worlds][n_robots] records (device / host memory),
+ * each held for steps_per_period world-steps.  Same result as n_periods x (set_commands + world_batch_step),
+ * but every world runs through all periods without a batch-wide barrier in between, so worlds that are
+ * expensive in one period do not stall the others (open-loop rollouts, pre-sampled action sequences).
+ * The last block stays installed as the current commands. */
+int world_batch_step_sequence(struct WorldBatch *batch, const struct RobotCommand *dev_cmds, int n_periods,
+                              int steps_per_period);
+int world_batch_step_sequence_host(struct WorldBatch *batch, const struct RobotCommand *host_cmds, int n_periods,
+                                   int steps_per_period);
 int world_batch_sync(struct WorldBatch *batch);
 
 /* ---- command input (no upstream implementation; schema grSim_Commands.proto).

@@ -110,6 +110,7 @@ BATCH_SYMBOLS = [
     ("world_batch_timestamp", C.c_double, [_VP]),
     ("world_batch_step", _I, [_VP, _I]), ("world_batch_step_delta", _I, [_VP, _I, _I, _F]),
     ("world_batch_sync", _I, [_VP]),
+    ("world_batch_step_sequence", _I, [_VP, _VP, _I, _I]), ("world_batch_step_sequence_host", _I, [_VP, _VP, _I, _I]),
     ("world_batch_set_commands", _I, [_VP, _VP]), ("world_batch_set_commands_device", _I, [_VP, _VP]),
     ("world_batch_clear_commands", _I, [_VP]), ("world_batch_gen_commands", _I, [_VP, _U64, _I]),
     ("world_batch_gen_commands_into", _I, [_VP, _VP, _U64, _I]),
@@ -256,6 +257,15 @@ class WorldBatch:
 
     def step_delta(self, n_steps, substeps, h):
         self._ck(lib().world_batch_step_delta(self._h, n_steps, substeps, C.c_float(float(h))))
+
+    def step_sequence(self, cmds, steps_per_period):
+        """cmds: host array [P, W, R] of CMD_DTYPE; one launch runs P periods of steps_per_period world-steps."""
+        cmds = np.ascontiguousarray(cmds, dtype=CMD_DTYPE)
+        assert cmds.ndim == 3 and cmds.shape[1] * cmds.shape[2] == self.W * self.R
+        self._ck(lib().world_batch_step_sequence_host(self._h, _ptr(cmds), cmds.shape[0], steps_per_period))
+
+    def step_sequence_device(self, dev_ptr, n_periods, steps_per_period):
+        self._ck(lib().world_batch_step_sequence(self._h, C.c_void_p(dev_ptr), n_periods, steps_per_period))
 
     def sync(self):
         self._ck(lib().world_batch_sync(self._h))

@@ -75,7 +75,7 @@ static void batch_free(WorldBatch *b) {
   for (World *w : b->views) delete w;
   cudaFree(b->d_pos); cudaFree(b->d_vel); cudaFree(b->d_aux); cudaFree(b->d_cmd);
   cudaFree(b->d_robot_ids); cudaFree(b->d_world_ids); cudaFree(b->d_gather); cudaFree(b->d_stats);
-  cudaFree(b->d_rep); cudaFree(b->d_field); cudaFree(b->d_prof);
+  cudaFree(b->d_rep); cudaFree(b->d_field); cudaFree(b->d_prof); cudaFree(b->d_seq);
   if (b->h_gather) cudaFreeHost(b->h_gather);
   for (cudaEvent_t e : b->kev) cudaEventDestroy(e);
   if (b->ev0) cudaEventDestroy(b->ev0);
@@ -141,13 +141,15 @@ WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_
   return b;
 }
 
-int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total) {
+int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total, int steps_per_period,
+                      long long cmd_period_stride) {
   ENTER(b);
   if (n_steps < 0 || substeps < 0) return SSLSIM_E_ARG;
   if (n_steps > 0 && substeps >= 0) {
     StepArgs a;
     a.pos = b->d_pos; a.vel = b->d_vel; a.aux = b->d_aux; a.cmd = b->cmd_active;
     a.n_worlds = b->W; a.n_robots = b->R; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
+    a.steps_per_period = steps_per_period; a.cmd_period_stride = cmd_period_stride;
     a.f = b->dfield; a.f_dev = b->d_field; a.p = b->params; a.prof = b->d_prof;
     if (b->ktiming) {
       if (b->kev_used + 2 > b->kev.size()) {
@@ -227,6 +229,33 @@ int world_batch_step(struct WorldBatch *b, int n_steps) {
 
 int world_batch_step_delta(struct WorldBatch *b, int n_steps, int substeps, float fixed_time_step) {
   return sslsim_batch_step(b, n_steps, substeps, fixed_time_step, fixed_time_step * (float)substeps);
+}
+
+int world_batch_step_sequence(struct WorldBatch *b, const struct RobotCommand *dev_cmds, int n_periods,
+                              int steps_per_period) {
+  ENTER(b);
+  if (!dev_cmds || n_periods <= 0 || steps_per_period <= 0) return SSLSIM_E_ARG;
+  const long long stride = (long long)b->W * b->R;
+  b->cmd_active = dev_cmds;
+  const int rc = sslsim_batch_step(b, n_periods * steps_per_period, 2, (float)(1.0 / 60 / 2), (float)(1.0 / 60),
+                                   steps_per_period, stride);
+  b->cmd_active = dev_cmds + (size_t)(n_periods - 1) * stride; /* the last block stays installed */
+  return rc;
+}
+
+int world_batch_step_sequence_host(struct WorldBatch *b, const struct RobotCommand *host_cmds, int n_periods,
+                                   int steps_per_period) {
+  ENTER(b);
+  if (!host_cmds || n_periods <= 0 || steps_per_period <= 0) return SSLSIM_E_ARG;
+  const size_t n = (size_t)n_periods * b->W * b->R;
+  if (n > b->seq_cap) {
+    CK(cudaStreamSynchronize(b->stream));
+    cudaFree(b->d_seq); b->d_seq = nullptr; b->seq_cap = 0;
+    CK(cudaMalloc(&b->d_seq, n * sizeof(RobotCommand)));
+    b->seq_cap = n;
+  }
+  CK(cudaMemcpyAsync(b->d_seq, host_cmds, n * sizeof(RobotCommand), cudaMemcpyHostToDevice, b->stream));
+  return world_batch_step_sequence(b, b->d_seq, n_periods, steps_per_period);
 }
 
 int world_batch_sync(struct WorldBatch *b) {

@@ -35,6 +35,7 @@ struct WorldBatch {
   float *h_gather = nullptr; /* pinned */
   unsigned long long *d_stats = nullptr;
   void *d_rep = nullptr; size_t rep_cap = 0;
+  RobotCommand *d_seq = nullptr; size_t seq_cap = 0; /* staging for host command sequences */
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -71,5 +72,6 @@ bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what);
 WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_robots, int cap_bodies, int device,
                                 uint64_t seed, uint64_t world0, int init_mode, const SslSimParams *params,
                                 bool run_init);
-int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total);
+int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total,
+                      int steps_per_period = 0, long long cmd_period_stride = 0);
 #endif

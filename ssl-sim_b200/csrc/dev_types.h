@@ -25,6 +25,8 @@ struct StepArgs {
   uint32_t *aux; /* [W][8] */
   const RobotCommand *cmd; /* [W][R] or NULL */
   int n_worlds, n_robots, n_steps, substeps;
+  int steps_per_period;         /* > 0: command sequence, a new [W][R] block every so many steps */
+  long long cmd_period_stride;  /* records between the blocks of a sequence */
   float h;
   DevField f;            /* by value: constant bank */
   const DevField *f_dev; /* the same in global memory, for the out-of-line general path */

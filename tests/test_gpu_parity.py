@@ -503,3 +503,24 @@ def test_referee_restart_placement(sim, orc):
     _compare(b.read_state(), o, 360)
     assert placed > W // 2 and int(o.aux[:, 3].sum()) == placed
     assert (np.abs(o.pos[:, R, 0]) <= 4.5 + 0.2).all()
+
+
+def test_command_sequence_in_one_launch(sim, orc):
+    """world_batch_step_sequence: P command periods in one launch == P x (set_commands + step)."""
+    W, R, P = 48, 12, 6
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    b.step(60); o.step(60)
+    seq = np.zeros((P, W, R), sim.CMD_DTYPE)
+    for p in range(P):
+        o.gen_commands(p, 1)
+        seq[p] = o.cmd
+    b.step_sequence(seq, 30)
+    for p in range(P):
+        o.cmd = seq[p].copy()
+        o.step(30)
+    _compare(b.read_state(), o, 30 * P)
+    assert b.frame_number == 60 + 30 * P
+    # the last block stays installed
+    b.step(10); o.step(10)
+    _compare(b.read_state(), o, 10)
