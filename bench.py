@@ -3,13 +3,15 @@
 
 Workload (BASELINE.json configs[1]): 4,096 batched 6v6 worlds per GPU on
 FIELD_2015 with randomized wheel-velocity commands that are redrawn every 30 world-steps.
-One bench *step* = one command batch + 30 world-steps of every world = ONE launch of the
-fused `step_worlds` kernel.  One world-step = one `world_step` of the reference
+One bench *step* = one command batch + 30 world-steps of every world.  One world-step = one `world_step` of the reference
 (reference src/sslsim.cpp:307-310: 1/60 s, two 1/120 s substeps).
 
-  value     device-resident arm: the K command batches are staged in HBM before the timed region;
-            each step is timed with CUDA events on the batch's own stream; L2 is flushed between
-            steps (outside the per-step event pairs).
+  value     device-resident arm: the K command batches are staged in HBM before the timed region and
+            consumed `--periods-per-launch` (default 10) at a time by one `step_worlds` launch
+            (world_batch_step_sequence: every world runs through its periods without a batch-wide
+            barrier); CUDA events bracket each launch on the batch's own stream; L2 is flushed between
+            launches (outside the event pairs).  `one_launch_per_period` is the same K steps with one
+            launch per command period -- what a closed-loop caller (and the e2e arm) does.
   e2e       the same work through the C ABI with HOST buffers: per step the command batch is copied
             from pinned host memory (world_batch_set_commands), stepped, and the per-world event /
             statistics words are read back (world_batch_read_aux); wall time of K steps.
@@ -381,7 +383,9 @@ def main():
                 # secondary ceiling: the kernel is issue/latency-bound, so also report warp-instructions issued per
                 # second against 148 SMs x 4 schedulers x SM clock (instruction count per world-step from the
                 # committed ncu capture of the 4096-world launch)
-                ipw = tj["warp_instructions_per_launch"] / (4096 * WORLD_STEPS_PER_STEP)
+                ipw = tj["warp_instructions_per_launch"] / tj.get("world_steps_per_launch", 4096 * WORLD_STEPS_PER_STEP)
+                if traffic is not None:   # scale the captured launch to this run's launch shape
+                    traffic = traffic * (W * WORLD_STEPS_PER_STEP * K / launches) / tj.get("world_steps_per_launch", 1)
                 peak_issue = 148 * 4 * (clocks.get("sm_max_mhz") or 1965) * 1e6
                 issue = {"warp_instructions_per_world_step": ipw, "achieved_per_s": ipw * value / world_size,
                          "peak_per_s": peak_issue, "frac": ipw * value / world_size / peak_issue,
@@ -400,8 +404,9 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "step_worlds", "algorithmic_bytes_per_launch": per_launch_bytes,
                          "bytes_per_world_step": bpws, "kernel_ms_per_launch": kern_ms_max / launches, "issue_ceiling": issue,
-                         "note": "latency/issue-bound fused kernel: state stays in registers for the 30 "
-                                 "world-steps of a launch; see DESIGN.md"},
+                         "note": "latency/issue-bound fused kernel: state stays in registers for all "
+                                 "world-steps of a launch (DRAM traffic = state once + one command block per "
+                                 "period); issue_ceiling is the informative bound; see DESIGN.md"},
             "cpu_baseline": cpu,
             "large_batch": large,
             "episode_stats": total_stats,

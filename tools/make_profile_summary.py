@@ -1,11 +1,12 @@
 """Turn gpurun_out/{launches.csv, prof_*.ncu-rep, bench_*.json} into the tracked summaries under profiles/.
-usage: python tools/make_profile_summary.py <tag> [ncu-rep] [launches.csv] [bench.json]"""
+usage: python tools/make_profile_summary.py <tag> [ncu-rep] [launches.csv] [bench.json] [world-steps per launch]"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 rep = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out/prof_r1.ncu-rep")
 launches = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out/launches.csv")
 bench = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "gpurun_out/bench_r1.json")
+WSPL = int(sys.argv[5]) if len(sys.argv) > 5 else 4096 * 30 * 10   # worlds x world-steps of one captured launch
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 
@@ -23,7 +24,8 @@ for r in rows[h + 1:]:
 tot = sum(sum(v) for v in agg.values())
 with open(os.path.join(out, tag + "_launches.txt"), "w") as f:
     f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 300: python bench.py --steps 20 --warmup 3 "
-            "--no-cpu-baseline --no-e2e (4096 6v6 worlds, 30 world-steps per step_worlds launch)\n")
+            "--no-cpu-baseline --no-e2e --large-worlds 0 (4096 6v6 worlds; warm-up and the per-period pass launch 30 "
+            "world-steps, the fused pass %d world-steps per step_worlds launch)\n" % (WSPL // 4096))
     f.write("per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes\n\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write("%-70s launches %3d  total %9.1f us  avg %8.1f us  share %5.1f%%\n" %
@@ -55,14 +57,16 @@ tr = sum(tobytes(r[ir], units[ir]) + tobytes(r[iw], units[iw]) for r in data) / 
 ii = hdr.index("smsp__inst_executed.sum")
 inst = sum(float(r[ii].replace(",", "")) for r in data) / len(data)
 json.dump({"dram_bytes_per_launch": tr, "warp_instructions_per_launch": inst,
-           "launch_shape": "4096 6v6 worlds x 30 world-steps", "kernel": "step_worlds", "source": os.path.basename(rep),
+           "world_steps_per_launch": WSPL, "launch_shape": "4096 6v6 worlds x %d world-steps" % (WSPL // 4096),
+           "kernel": "step_worlds", "source": os.path.basename(rep),
            "how": "dram__bytes_read.sum + dram__bytes_write.sum, mean over %d captured launches, ncu --set full" % len(data)},
           open(os.path.join(out, "traffic.json"), "w"), indent=1)
 
 # 3. per-line / footprint breakdowns
 for tool, name in (("ncu_lines.py", "_step_worlds_lines.txt"), ("icache_footprint.py", "_step_worlds_icache.txt"),
                    ("sass_freq.py", "_step_worlds_sass_freq.txt")):
-    args = [sys.executable, os.path.join(ROOT, "tools", tool), rep] + (["40"] if tool == "ncu_lines.py" else ["122880"])
+    # warp-substeps per launch = (worlds / 2 warps) x (2 substeps per step) x steps = worlds x steps
+    args = [sys.executable, os.path.join(ROOT, "tools", tool), rep] + (["40"] if tool == "ncu_lines.py" else [str(WSPL)])
     txt = subprocess.run(args, capture_output=True, text=True).stdout
     open(os.path.join(out, tag + name), "w").write(txt)
 if os.path.exists(bench):
