@@ -100,10 +100,19 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(self.period)
 
+    def _sample_once(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+
     def finish(self):
         self._halt.set()
         if self.is_alive():
             self.join(timeout=1.0)
+        if self.ok and not self.samples:   # a very short timed region: the GPU is still at its load clock right after it
+            try:
+                self._sample_once()
+            except Exception:
+                pass
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
