@@ -21,8 +21,13 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def sim():
-    """The product package (ctypes binding of libsslsim_b200.so)."""
-    return importlib.import_module("ssl-sim_b200")
+    """The product package (ctypes binding of libsslsim_b200.so).  The library is normally built by
+    __graft_entry__.build(); if it is missing (fresh checkout) it is compiled here -- building is not a fallback,
+    the calls still go to the CUDA library only."""
+    mod = importlib.import_module("ssl-sim_b200")
+    if not os.path.exists(mod.LIB_PATH):
+        mod.build()
+    return mod
 
 
 @pytest.fixture(scope="session")
