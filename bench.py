@@ -218,6 +218,8 @@ def main():
     import torch.distributed as dist
 
     sim = importlib.import_module("ssl-sim_b200")
+    if not os.path.exists(sim.LIB_PATH):
+        sim.build()   # fresh checkout: compile the CUDA library (nvcc); there is still no fallback path
     sim.lib()  # fails loudly if the CUDA library is missing: there is no fallback
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")

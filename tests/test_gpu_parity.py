@@ -524,3 +524,48 @@ def test_command_sequence_in_one_launch(sim, orc):
     # the last block stays installed
     b.step(10); o.step(10)
     _compare(b.read_state(), o, 10)
+
+
+def test_legacy_accessors_on_batch_members(sim, orc):
+    """The upstream TODO stubs (reference src/sslsim.cpp:390-428, 452-471) implemented, used on members of a
+    batch through world_batch_get_world: getters mirror the device state, setters write through."""
+    L = sim.lib()
+    W, R = 8, 12
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    o.gen_commands(0, 1); b.set_commands(o.cmd)
+    b.step(120); o.step(120)
+    w5 = b.get_world(5)
+    assert w5.robot_count == R and w5.frame_number == 120
+    # getters
+    for i in (0, 7, 11):
+        p = L.robot_get_pos(w5.robot(i)); v = L.robot_get_vel(w5.robot(i))
+        assert (np.float32(p.x), np.float32(p.y), np.float32(p.w)) == tuple(o.pos[5, i, [0, 1, 3]])
+        assert (np.float32(v.x), np.float32(v.y), np.float32(v.w)) == tuple(o.vel[5, i, [0, 1, 3]])
+        assert np.float32(L.robot_get_speed2(w5.robot(i))) == np.float32(np.float32(np.float32(o.vel[5, i, 0] * o.vel[5, i, 0]) + np.float32(o.vel[5, i, 1] * o.vel[5, i, 1])) + np.float32(o.vel[5, i, 2] * o.vel[5, i, 2]))
+    bp, bv = L.ball_get_pos(w5.ball()), L.ball_get_vel(w5.ball())
+    assert (np.float32(bp.x), np.float32(bp.y), np.float32(bp.z)) == tuple(o.pos[5, R, :3])
+    assert (np.float32(bv.x), np.float32(bv.y), np.float32(bv.z)) == tuple(o.vel[5, R, :3])
+    peak = np.frombuffer(o.aux[5, 1:2].tobytes(), np.float32)[0]
+    assert np.float32(L.ball_get_peak_speed2_from_last_kick(w5.ball())) == peak
+    last = int(o.aux[5, 0]) & 0xFF
+    lt = L.ball_last_touching_robot(w5.ball())
+    assert (lt is None) == (last == 0xFF)
+    if lt is not None:
+        assert L.get_id(lt) == last // 2 and L.get_team(lt) == last % 2
+    for i in range(R):
+        assert L.ball_is_touching_robot(w5.ball(), w5.robot(i)) == ((int(o.aux[5, 2]) >> i) & 1)
+    # setters write through to the device and only touch their world
+    L.ball_set_pos(w5.ball(), sim.Pos3(1.0, -1.0, 0.3, 0, 0, 0))
+    L.ball_set_vel(w5.ball(), sim.Pos3(2.0, 0.5, 1.0, 0, 0, 0))
+    L.robot_set_vel(w5.robot(2), sim.Pos2(-1.0, 0.25, 3.0))
+    o.pos[5, R, :3] = (1.0, -1.0, 0.3); o.vel[5, R, :3] = (2.0, 0.5, 1.0)
+    o.vel[5, 2, [0, 1, 3]] = (-1.0, 0.25, 3.0)
+    # two robots side by side: touching by geometry
+    w2 = b.get_world(2)
+    L.robot_set_pos(w2.robot(0), sim.Pos2(0.0, 2.0, 0.0)); L.robot_set_pos(w2.robot(1), sim.Pos2(0.19, 2.0, 0.0))
+    assert L.robot_is_touching_robot(w2.robot(0), w2.robot(1)) == 1 and L.robot_is_touching_robot(w2.robot(0), w2.robot(5)) in (0, 1)
+    o.pos[2, 0] = (0.0, 2.0, 0.5, 0.0); o.pos[2, 1] = (0.19, 2.0, 0.5, 0.0)
+    b.step(45); o.step(45)
+    _compare(b.read_state(), o, 45)
+    assert w5.frame_number == 165 and np.float32(w5.ball_vec()[0]) == o.pos[5, R, 0]
