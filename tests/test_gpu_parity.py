@@ -569,3 +569,18 @@ def test_legacy_accessors_on_batch_members(sim, orc):
     b.step(45); o.step(45)
     _compare(b.read_state(), o, 45)
     assert w5.frame_number == 165 and np.float32(w5.ball_vec()[0]) == o.pos[5, R, 0]
+
+
+@pytest.mark.parametrize("fld,iters", [("FIELD_2014_SINGLE", 10), ("FIELD_2014_DOUBLE", 4), ("FIELD_2015", 20), ("FIELD_DIV_A", 1)])
+def test_other_fields_and_iteration_counts(sim, orc, fld, iters):
+    """The reference's other field constants (src/field.c:11-45) and solver iteration counts other than Bullet's 10."""
+    W, R = 48, 12
+    b = sim.WorldBatch(W, R, fld=fld, params=sim.default_params(solver_iterations=iters))
+    o = orc.Worlds(W, R, fld=getattr(orc, fld), params=orc.default_params(solver_iterations=iters))
+    pos, vel, aux = b.read_state()
+    np.testing.assert_array_equal(pos, o.pos)
+    for period in range(8):
+        o.gen_commands(period, 1)
+        b.gen_commands(period, 1)
+        b.step(30); o.step(30)
+    _compare(b.read_state(), o, 240, "%s iters=%d" % (fld, iters))
