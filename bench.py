@@ -12,9 +12,14 @@ One bench *step* = one command batch + 30 world-steps of every world.  One world
             barrier); CUDA events bracket each launch on the batch's own stream; L2 is flushed between
             launches (outside the event pairs).  `one_launch_per_period` is the same K steps with one
             launch per command period -- what a closed-loop caller (and the e2e arm) does.
-  e2e       the same work through the C ABI with HOST buffers: per step the command batch is copied
-            from pinned host memory (world_batch_set_commands), stepped, and the per-world event /
-            statistics words are read back (world_batch_read_aux); wall time of K steps.
+  e2e       the same work through the C ABI with HOST buffers, closed loop: per step the command batch is
+            copied from pinned host memory, stepped, and the per-world event / statistics words are read
+            back to host memory; wall time of K steps.  The batch is driven as `--e2e-chunks` (default 8)
+            contiguous chunks of worlds, each on its own CUDA stream (world_batch_chunk_step /
+            world_batch_chunk_wait): the host waits for a chunk's results of step k before it submits
+            that chunk's step k+1, while the other chunks' copies and launches keep the GPU busy.
+            `e2e.whole_batch` is the same loop with one stream and a batch-wide barrier per step
+            (world_batch_set_commands + world_batch_step + world_batch_read_aux).
   roofline  algorithmic bytes (1,232 B per 6v6 world-step) / kernel duration vs the
             measured HBM copy bandwidth.
   cpu_baseline  the CPU oracle (restated-Bullet port; Bullet itself is not buildable here) on the
@@ -198,6 +203,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8,
+                    help="e2e arm: chunks of worlds, each on its own stream (1 = whole batch, one barrier per step)")
     ap.add_argument("--periods-per-launch", type=int, default=10,
                     help="device-resident arm: command periods (bench steps) fused into one step_worlds launch")
     ap.add_argument("--large-worlds", type=int, default=131072,
@@ -319,26 +326,56 @@ def main():
         hp, ap_ = host_cmd.data_ptr(), host_aux.data_ptr()
         L, h = sim.lib(), b._h
 
-        def e2e_step(k):
+        def whole_step(k):
             L.world_batch_set_commands(h, C.c_void_p(hp + (k % n_host) * cmd_bytes))   # H2D, pinned
             L.world_batch_step(h, WORLD_STEPS_PER_STEP)
             rc = L.world_batch_read_aux(h, C.c_void_p(ap_))                            # D2H + sync
             if rc < 0:
                 raise RuntimeError("e2e step failed: %d" % rc)
-        for k in range(WU):
-            e2e_step(k)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(K):
-            e2e_step(WU + k)
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": units / float(te[0]), "unit": "world-steps/s", "h2d_bytes_per_step": cmd_bytes,
-               "d2h_bytes_per_step": W * 32, "ms_per_step": float(te[0]) * 1e3 / K,
-               "api": "world_batch_set_commands(host) + world_batch_step(30) + world_batch_read_aux(host)"}
+
+        def timed(step_fn):
+            for k in range(WU):
+                step_fn(k)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(K):
+                step_fn(WU + k)
+            barrier()                      # every chunk's last results are in host memory
+            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if distributed:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te[0])
+
+        snap = b.snapshot()
+        whole_s = timed(whole_step)
+        e2e_s, api = whole_s, "world_batch_set_commands(host) + world_batch_step(30) + world_batch_read_aux(host)"
+        nch = max(1, min(args.e2e_chunks, W))
+        if nch > 1:
+            stats_whole = b.reduce_stats()
+            b.restore(snap)
+            b.set_chunks(nch)
+            ranges = [b.chunk_range(c) for c in range(nch)]
+
+            def chunk_step(k):
+                base = hp + (k % n_host) * cmd_bytes
+                for c, (first, count) in enumerate(ranges):
+                    # closed loop: this chunk's results of the previous step are in host memory before its next
+                    # commands are submitted; the other chunks' queued work overlaps the wait
+                    if L.world_batch_chunk_wait(h, c) < 0 or L.world_batch_chunk_step(
+                            h, c, C.c_void_p(base + first * R * 32), WORLD_STEPS_PER_STEP,
+                            C.c_void_p(ap_ + first * 32)) < 0:
+                        raise RuntimeError("e2e chunk step failed")
+            e2e_s = timed(chunk_step)
+            assert b.reduce_stats() == stats_whole, "chunked and whole-batch stepping must produce identical worlds"
+            b.set_chunks(0)
+            api = ("%d chunks x [world_batch_chunk_wait + world_batch_chunk_step(host commands, 30, host aux)], "
+                   "one CUDA stream per chunk" % nch)
+        b.free_snapshot(snap)
+        e2e = {"value": units / e2e_s, "unit": "world-steps/s", "h2d_bytes_per_step": cmd_bytes,
+               "d2h_bytes_per_step": W * 32, "ms_per_step": e2e_s * 1e3 / K, "chunks": nch, "api": api,
+               "whole_batch": {"value": units / whole_s, "ms_per_step": whole_s * 1e3 / K,
+                               "api": "world_batch_set_commands(host) + world_batch_step(30) + "
+                                      "world_batch_read_aux(host), one barrier per step"}}
 
     # ---- extra: the per-GPU shard of configs[4] (1,048,576 worlds over 8 GPUs = 131,072 per GPU) ---------------
     large = None

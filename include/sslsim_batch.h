@@ -135,6 +135,24 @@ int world_batch_step_sequence_host(struct WorldBatch *batch, const struct RobotC
                                    int steps_per_period);
 int world_batch_sync(struct WorldBatch *batch);
 
+/* ---- pipelined closed loop.  The reference's caller is a loop of "read commands, world_step, send state"
+ * (src/main.c:79-96); with thousands of worlds the batch-wide barrier of that loop (every world waits for the
+ * slowest one, and for the copies) is what limits it.  world_batch_set_chunks splits the batch into n contiguous
+ * ranges of worlds, each with its own CUDA stream.  world_batch_chunk_step queues on the chunk's stream: the
+ * H2D copy of the chunk's commands (host_cmds = [chunk worlds][n_robots] records, pinned memory for a truly
+ * asynchronous copy; NULL keeps the installed ones), n_steps world-steps of the chunk's worlds, and the D2H copy
+ * of their aux words into host_aux ([chunk worlds][8], may be NULL) -- and returns at once.
+ * world_batch_chunk_wait blocks until that work is done and host_aux is valid.  A closed-loop caller cycles
+ * over the chunks (wait c, decide, submit c): copies, launches and the tail of each launch overlap with the
+ * other chunks' work.  Results are bit-identical to whole-batch stepping.  Every other call on the batch is
+ * ordered after all queued chunk work; n_chunks 0 or 1 switches the pipeline off. */
+int world_batch_set_chunks(struct WorldBatch *batch, int n_chunks);
+int world_batch_chunk_count(const struct WorldBatch *batch);
+int world_batch_chunk_range(const struct WorldBatch *batch, int chunk, int *first_world, int *n_worlds);
+int world_batch_chunk_step(struct WorldBatch *batch, int chunk, const struct RobotCommand *host_cmds, int n_steps,
+                           uint32_t *host_aux);
+int world_batch_chunk_wait(struct WorldBatch *batch, int chunk);
+
 /* ---- command input (no upstream implementation; schema grSim_Commands.proto).
  * host/device array of n_worlds * n_robots records, world-major.  NULL (or
  * world_batch_clear_commands) = every robot passive, i.e. reference mode. */

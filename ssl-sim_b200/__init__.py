@@ -110,6 +110,9 @@ BATCH_SYMBOLS = [
     ("world_batch_timestamp", C.c_double, [_VP]),
     ("world_batch_step", _I, [_VP, _I]), ("world_batch_step_delta", _I, [_VP, _I, _I, _F]),
     ("world_batch_sync", _I, [_VP]),
+    ("world_batch_set_chunks", _I, [_VP, _I]), ("world_batch_chunk_count", _I, [_VP]),
+    ("world_batch_chunk_range", _I, [_VP, _I, C.POINTER(_I), C.POINTER(_I)]),
+    ("world_batch_chunk_step", _I, [_VP, _I, _VP, _I, _VP]), ("world_batch_chunk_wait", _I, [_VP, _I]),
     ("world_batch_step_sequence", _I, [_VP, _VP, _I, _I]), ("world_batch_step_sequence_host", _I, [_VP, _VP, _I, _I]),
     ("world_batch_set_commands", _I, [_VP, _VP]), ("world_batch_set_commands_device", _I, [_VP, _VP]),
     ("world_batch_clear_commands", _I, [_VP]), ("world_batch_gen_commands", _I, [_VP, _U64, _I]),
@@ -269,6 +272,22 @@ class WorldBatch:
 
     def sync(self):
         self._ck(lib().world_batch_sync(self._h))
+
+    # ---- chunked pipeline (closed loop without a batch-wide barrier) ----
+    def set_chunks(self, n_chunks):
+        self._ck(lib().world_batch_set_chunks(self._h, n_chunks))
+
+    def chunk_range(self, chunk):
+        first, count = C.c_int(0), C.c_int(0)
+        self._ck(lib().world_batch_chunk_range(self._h, chunk, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def chunk_step(self, chunk, host_cmd_ptr, n_steps, host_aux_ptr):
+        """queue H2D(commands of the chunk) + n_steps + D2H(aux of the chunk) on the chunk's stream; returns at once"""
+        self._ck(lib().world_batch_chunk_step(self._h, chunk, host_cmd_ptr, n_steps, host_aux_ptr))
+
+    def chunk_wait(self, chunk):
+        self._ck(lib().world_batch_chunk_wait(self._h, chunk))
 
     def reset(self, seed=None, init_mode=0):
         self._ck(lib().world_batch_reset(self._h, self.seed if seed is None else seed, init_mode))

@@ -63,14 +63,37 @@ bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what) {
   do {                                                             \
     if (!sslsim_check(b, (call), #call)) return SSLSIM_E_CUDA;     \
   } while (0)
-#define ENTER(b)                                  \
+/* work queued on chunk streams is ordered before anything that follows on the batch stream */
+static int join_chunks(WorldBatch *b) {
+  for (WorldBatch::Chunk &c : b->chunks) {
+    if (!c.dirty) continue;
+    if (!sslsim_check(b, cudaEventRecord(c.done, c.stream), "chunk record") ||
+        !sslsim_check(b, cudaStreamWaitEvent(b->stream, c.done, 0), "chunk join")) return SSLSIM_E_CUDA;
+    c.dirty = false;
+  }
+  return SSLSIM_OK;
+}
+#define ENTER_NOJOIN(b)                           \
   if (!(b)) return SSLSIM_E_ARG;                  \
   if ((b)->last_error == SSLSIM_E_CUDA) return SSLSIM_E_CUDA; \
   cudaSetDevice((b)->device)
+#define ENTER(b)                                  \
+  ENTER_NOJOIN(b);                                \
+  if (!(b)->chunks.empty() && join_chunks(b)) return SSLSIM_E_CUDA
+
+static void free_chunks(WorldBatch *b) {
+  for (WorldBatch::Chunk &c : b->chunks) {
+    if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
+    if (c.done) cudaEventDestroy(c.done);
+  }
+  b->chunks.clear();
+}
 
 static void batch_free(WorldBatch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  free_chunks(b);
+  if (b->ev_main) cudaEventDestroy(b->ev_main);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (World *w : b->views) delete w;
   cudaFree(b->d_pos); cudaFree(b->d_vel); cudaFree(b->d_aux); cudaFree(b->d_cmd);
@@ -141,16 +164,24 @@ WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_
   return b;
 }
 
+static StepArgs step_args(const WorldBatch *b, int first, int count, const RobotCommand *cmd, int n_steps, int substeps,
+                          float h, int steps_per_period, long long cmd_period_stride) {
+  const size_t N = (size_t)b->R + 1;
+  StepArgs a;
+  a.pos = b->d_pos + first * N; a.vel = b->d_vel + first * N; a.aux = b->d_aux + (size_t)first * 8;
+  a.cmd = cmd ? cmd + (size_t)first * b->R : nullptr;
+  a.n_worlds = count; a.n_robots = b->R; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
+  a.steps_per_period = steps_per_period; a.cmd_period_stride = cmd_period_stride;
+  a.f = b->dfield; a.f_dev = b->d_field; a.p = b->params; a.prof = b->d_prof;
+  return a;
+}
+
 int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total, int steps_per_period,
                       long long cmd_period_stride) {
   ENTER(b);
   if (n_steps < 0 || substeps < 0) return SSLSIM_E_ARG;
   if (n_steps > 0 && substeps >= 0) {
-    StepArgs a;
-    a.pos = b->d_pos; a.vel = b->d_vel; a.aux = b->d_aux; a.cmd = b->cmd_active;
-    a.n_worlds = b->W; a.n_robots = b->R; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
-    a.steps_per_period = steps_per_period; a.cmd_period_stride = cmd_period_stride;
-    a.f = b->dfield; a.f_dev = b->d_field; a.p = b->params; a.prof = b->d_prof;
+    const StepArgs a = step_args(b, 0, b->W, b->cmd_active, n_steps, substeps, h, steps_per_period, cmd_period_stride);
     if (b->ktiming) {
       if (b->kev_used + 2 > b->kev.size()) {
         for (int k = 0; k < 2; ++k) {
@@ -259,8 +290,72 @@ int world_batch_step_sequence_host(struct WorldBatch *b, const struct RobotComma
 }
 
 int world_batch_sync(struct WorldBatch *b) {
-  ENTER(b);
+  ENTER(b); /* joins the chunk streams first */
   CK(cudaStreamSynchronize(b->stream));
+  return SSLSIM_OK;
+}
+
+/* ---- chunked pipeline -------------------------------------------------------------------------------------- */
+int world_batch_set_chunks(struct WorldBatch *b, int n_chunks) {
+  ENTER(b);
+  if (n_chunks < 0 || n_chunks > b->W || n_chunks > 256) return SSLSIM_E_ARG;
+  CK(cudaStreamSynchronize(b->stream));
+  free_chunks(b);
+  if (n_chunks <= 1) return SSLSIM_OK;
+  if (!b->ev_main) CK(cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming));
+  if (!b->d_cmd && b->R > 0) CK(cudaMalloc(&b->d_cmd, (size_t)b->W * b->R * sizeof(RobotCommand)));
+  b->chunks.resize(n_chunks);
+  for (int c = 0; c < n_chunks; ++c) {
+    WorldBatch::Chunk &k = b->chunks[c];
+    k.first = (int)((long long)b->W * c / n_chunks);
+    k.count = (int)((long long)b->W * (c + 1) / n_chunks) - k.first;
+    CK(cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
+  }
+  return SSLSIM_OK;
+}
+
+int world_batch_chunk_count(const struct WorldBatch *b) { return b ? (int)b->chunks.size() : 0; }
+
+int world_batch_chunk_range(const struct WorldBatch *b, int chunk, int *first_world, int *n_worlds) {
+  if (!b || chunk < 0 || chunk >= (int)b->chunks.size()) return SSLSIM_E_ARG;
+  if (first_world) *first_world = b->chunks[chunk].first;
+  if (n_worlds) *n_worlds = b->chunks[chunk].count;
+  return SSLSIM_OK;
+}
+
+int world_batch_chunk_step(struct WorldBatch *b, int chunk, const struct RobotCommand *host_cmds, int n_steps,
+                           uint32_t *host_aux) {
+  ENTER_NOJOIN(b);
+  if (chunk < 0 || chunk >= (int)b->chunks.size() || n_steps < 0) return SSLSIM_E_ARG;
+  WorldBatch::Chunk &k = b->chunks[chunk];
+  /* after whatever was queued on the batch stream before this call */
+  CK(cudaEventRecord(b->ev_main, b->stream));
+  CK(cudaStreamWaitEvent(k.stream, b->ev_main, 0));
+  if (host_cmds && b->R > 0) {
+    CK(cudaMemcpyAsync(b->d_cmd + (size_t)k.first * b->R, host_cmds, (size_t)k.count * b->R * sizeof(RobotCommand),
+                       cudaMemcpyHostToDevice, k.stream));
+    b->cmd_active = b->d_cmd;
+  }
+  if (n_steps > 0) {
+    const StepArgs a = step_args(b, k.first, k.count, b->cmd_active, n_steps, 2, (float)(1.0 / 60 / 2), 0, 0);
+    CK(sslsim_launch_step(a, b->lanes, k.stream));
+  }
+  if (host_aux)
+    CK(cudaMemcpyAsync(host_aux, b->d_aux + (size_t)k.first * 8, (size_t)k.count * 8 * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, k.stream));
+  k.dirty = true;
+  if (chunk == 0) { /* the batch clock follows chunk 0; a caller keeps the chunks within one period of each other */
+    for (int s = 0; s < n_steps; ++s) { b->timestamp += (float)(1.0 / 60); b->frame++; }
+  }
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+int world_batch_chunk_wait(struct WorldBatch *b, int chunk) {
+  ENTER_NOJOIN(b);
+  if (chunk < 0 || chunk >= (int)b->chunks.size()) return SSLSIM_E_ARG;
+  CK(cudaStreamSynchronize(b->chunks[chunk].stream));
   return SSLSIM_OK;
 }
 
@@ -538,12 +633,12 @@ int world_batch_kernel_time(struct WorldBatch *b, float *total_ms, int *launches
 int world_batch_profile_counters(struct WorldBatch *b, unsigned *out) {
   ENTER(b);
   if (!b->d_prof) {
-    CK(cudaMalloc(&b->d_prof, (size_t)b->W * 8 * sizeof(unsigned)));
-    CK(cudaMemset(b->d_prof, 0, (size_t)b->W * 8 * sizeof(unsigned)));
+    CK(cudaMalloc(&b->d_prof, (size_t)b->W * 16 * sizeof(unsigned)));
+    CK(cudaMemset(b->d_prof, 0, (size_t)b->W * 16 * sizeof(unsigned)));
     return 1;
   }
   CK(cudaStreamSynchronize(b->stream));
-  CK(cudaMemcpy(out, b->d_prof, (size_t)b->W * 8 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, b->d_prof, (size_t)b->W * 16 * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return SSLSIM_OK;
 }
 #endif

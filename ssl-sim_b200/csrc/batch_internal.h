@@ -50,6 +50,10 @@ struct WorldBatch {
   std::vector<int> robot_ids; /* per robot slot */
   std::vector<int> robot_teams;
   std::vector<World *> views;
+  /* chunked pipeline (world_batch_set_chunks): contiguous world ranges, one stream each */
+  struct Chunk { int first = 0, count = 0; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; bool dirty = false; };
+  std::vector<Chunk> chunks;
+  cudaEvent_t ev_main = nullptr; /* orders chunk work after earlier work on the batch stream */
 };
 
 struct World {

@@ -526,6 +526,44 @@ def test_command_sequence_in_one_launch(sim, orc):
     _compare(b.read_state(), o, 10)
 
 
+@pytest.mark.parametrize("n_chunks", [2, 5])
+def test_chunked_pipeline_matches_whole_batch(sim, orc, n_chunks):
+    """world_batch_set_chunks / chunk_step / chunk_wait: a closed loop cycling over chunks (each with its own
+    stream, chunks up to one period apart) gives the same worlds and the same per-period aux words as the
+    oracle stepping the whole batch."""
+    import ctypes as C
+    W, R, P = 50, 12, 5
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    b.step(60); o.step(60)
+    cmds = np.zeros((P, W, R), sim.CMD_DTYPE)
+    aux_ref = np.zeros((P, W, 8), np.uint32)
+    for p in range(P):
+        o.gen_commands(p, 1)
+        cmds[p] = o.cmd
+        o.step(30)
+        aux_ref[p] = o.aux
+    b.set_chunks(n_chunks)
+    ranges = [b.chunk_range(c) for c in range(n_chunks)]
+    assert ranges[0][0] == 0 and sum(n for _, n in ranges) == W
+    assert all(ranges[c][0] + ranges[c][1] == ranges[c + 1][0] for c in range(n_chunks - 1))
+    aux = np.zeros((P, W, 8), np.uint32)
+    for p in range(P):
+        for c, (first, count) in enumerate(ranges):
+            if p > 0:
+                b.chunk_wait(c)      # closed loop: the results of period p-1 of this chunk are in host memory now
+                np.testing.assert_array_equal(aux[p - 1, first:first + count], aux_ref[p - 1, first:first + count])
+            blk = np.ascontiguousarray(cmds[p, first:first + count])   # pageable: the runtime stages it before returning
+            b.chunk_step(c, blk.ctypes.data_as(C.c_void_p), 30, aux[p, first:first + count].ctypes.data_as(C.c_void_p))
+    b.sync()                       # joins every chunk stream
+    np.testing.assert_array_equal(aux[P - 1], aux_ref[P - 1])
+    _compare(b.read_state(), o, 30 * P)
+    assert b.frame_number == 60 + 30 * P
+    b.set_chunks(0)                # back to whole-batch stepping
+    b.step(10); o.step(10)
+    _compare(b.read_state(), o, 10)
+
+
 def test_legacy_accessors_on_batch_members(sim, orc):
     """The upstream TODO stubs (reference src/sslsim.cpp:390-428, 452-471) implemented, used on members of a
     batch through world_batch_get_world: getters mirror the device state, setters write through."""

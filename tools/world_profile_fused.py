@@ -14,7 +14,7 @@ for p in range(1, 120):
 stage = torch.empty(P * W * R * 32, dtype=torch.uint8, device="cuda")
 for k in range(P):
     b.gen_commands_into(stage.data_ptr() + k * W * R * 32, 1000 + k, 0)
-out = np.zeros((W, 8), np.uint32)
+out = np.zeros((W, 16), np.uint32)
 L.world_batch_profile_counters(b._h, None)
 b.sync(); b.timer_start(); b.step_sequence_device(stage.data_ptr(), P, 30); ms = b.timer_stop()
 L.world_batch_profile_counters(b._h, out.ctypes.data_as(C.c_void_p))
@@ -22,6 +22,9 @@ names = ["cycles", "generic_substeps", "pair_substeps", "iterations", "levels", 
 cyc = out[:, 0].astype(np.float64)
 print("fused launch %.3f ms (%d substeps); cycles mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f" %
       (ms, P * 60, cyc.mean(), np.percentile(cyc, 50), np.percentile(cyc, 90), np.percentile(cyc, 99), cyc.max()))
+sec = ["actuation", "row_setup", "broadphase", "pair_rows", "solve", "rest"]
 for w in np.argsort(-cyc)[:10]:
     print("  world %5d " % w + " ".join("%s=%d" % (n, v) for n, v in zip(names[:7], out[w])))
+    print("              per substep: " + " ".join("%s=%d" % (n, v / (P * 60)) for n, v in zip(sec, out[w, 8:14])))
+print("mean per substep: " + " ".join("%s=%.0f" % (n, v / (P * 60)) for n, v in zip(sec, out[:, 8:14].mean(0))))
 print("means:", " ".join("%s=%.1f" % (n, v) for n, v in zip(names[:7], out[:, :7].mean(0))))
