@@ -46,6 +46,7 @@
 #define SPLIT_THRESH (-0.04f)
 #define REST_THRESH 0.2f      /* restitution velocity threshold (Bullet >= 2.87 default) */
 #define FLT_EPS 1.1920929e-07f
+#define L2_MAX 1e37f /* squared lateral speed above which the direction falls back like a zero one (overflow guard) */
 #define TWO_PI 6.2831855f
 /* wheel mounting angles: reference :27-28 rotates by WHEELS_ANGLE about (0,0,-1) */
 static const float WSIN[4] = {-0.8660254f, -0.70710677f, 0.70710677f, 0.8660254f};
@@ -205,7 +206,7 @@ static void finish_row(const gen_ctx *g, row_t *r, float nx, float ny, float nz,
   /* single friction direction along the lateral relative velocity */
   float lx = rvx - nx * vn, ly = rvy - ny * vn, lz = rvz - nz * vn;
   float l2 = lx * lx + ly * ly + lz * lz;
-  if (l2 > FLT_EPS) {
+  if (l2 > FLT_EPS && l2 < L2_MAX) {
     float k = 1.0f / sqrtf(l2);
     r->tx = lx * k; r->ty = ly * k; r->tz = lz * k;
   } else {
@@ -230,7 +231,7 @@ static int gen_ground(const gen_ctx *g, int b, row_t *r) {
     float cvx = g->vel[b].x - BALL_R * g->vel[b].w; /* vel.w = omega_y */
     float cvy = g->vel[b].y + BALL_R * g->pos[b].w; /* pos.w = omega_x */
     float l2 = cvx * cvx + cvy * cvy;
-    if (l2 > FLT_EPS) {
+    if (l2 > FLT_EPS && l2 < L2_MAX) {
       float k = 1.0f / sqrtf(l2);
       r->tx = cvx * k; r->ty = cvy * k; r->tz = 0.0f;
     } else {

@@ -633,12 +633,12 @@ int world_batch_kernel_time(struct WorldBatch *b, float *total_ms, int *launches
 int world_batch_profile_counters(struct WorldBatch *b, unsigned *out) {
   ENTER(b);
   if (!b->d_prof) {
-    CK(cudaMalloc(&b->d_prof, (size_t)b->W * 16 * sizeof(unsigned)));
-    CK(cudaMemset(b->d_prof, 0, (size_t)b->W * 16 * sizeof(unsigned)));
+    CK(cudaMalloc(&b->d_prof, (size_t)b->W * 32 * sizeof(unsigned)));
+    CK(cudaMemset(b->d_prof, 0, (size_t)b->W * 32 * sizeof(unsigned)));
     return 1;
   }
   CK(cudaStreamSynchronize(b->stream));
-  CK(cudaMemcpy(out, b->d_prof, (size_t)b->W * 16 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, b->d_prof, (size_t)b->W * 32 * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return SSLSIM_OK;
 }
 #endif

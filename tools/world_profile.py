@@ -11,7 +11,7 @@ b = sim.WorldBatch(W, R)
 b.gen_commands(0, 0); b.step(120)
 for p in range(1, int(sys.argv[1]) if len(sys.argv) > 1 else 120):
     b.gen_commands(p, 0); b.step(30)
-out = np.zeros((W, 16), np.uint32)
+out = np.zeros((W, 32), np.uint32)
 L.world_batch_profile_counters(b._h, None)     # allocates the counter buffer
 b.gen_commands(1000, 0); b.timer_start(); b.step(30); ms = b.timer_stop()
 L.world_batch_profile_counters(b._h, out.ctypes.data_as(C.c_void_p))
