@@ -225,6 +225,12 @@ int world_batch_kernel_time(struct WorldBatch *batch, float *total_ms, int *laun
 /* tuning: lanes per world (16 or 32; 0 = automatic) */
 int world_batch_set_lanes_per_world(struct WorldBatch *batch, int lanes);
 
+/* self-test: the step kernel computes its square roots and divisions with branch-free sequences that are
+ * correctly rounded on the operand ranges it guarantees; this counts mismatches against sqrtf and operator/ over
+ * n random operands from those ranges (expected: 0 and 0) */
+int sslsim_selftest_math(int device, unsigned long long n, unsigned long long seed, unsigned long long *bad_sqrt,
+                         unsigned long long *bad_div);
+
 int world_batch_last_error(const struct WorldBatch *batch);
 const char *world_batch_error_string(const struct WorldBatch *batch);
 const char *sslsim_b200_version(void);

@@ -132,6 +132,7 @@ BATCH_SYMBOLS = [
     ("world_batch_enable_kernel_timing", _I, [_VP, _I]),
     ("world_batch_kernel_time", _I, [_VP, C.POINTER(_F), C.POINTER(_I), _I]),
     ("world_batch_set_lanes_per_world", _I, [_VP, _I]),
+    ("sslsim_selftest_math", _I, [_I, _U64, _U64, C.POINTER(_U64), C.POINTER(_U64)]),
     ("world_batch_last_error", _I, [_VP]), ("world_batch_error_string", C.c_char_p, [_VP]),
     ("sslsim_b200_version", C.c_char_p, []),
 ]

@@ -643,6 +643,22 @@ int world_batch_profile_counters(struct WorldBatch *b, unsigned *out) {
 }
 #endif
 
+/* self-test hook: mismatches of the kernel's branch-free sqrt / division against sqrtf and operator/ */
+int sslsim_selftest_math(int device, unsigned long long n, unsigned long long seed, unsigned long long *bad_sqrt,
+                         unsigned long long *bad_div) {
+  if (cudaSetDevice(device) != cudaSuccess) return SSLSIM_E_CUDA;
+  unsigned long long *d = nullptr, h[2] = {0, 0};
+  if (cudaMalloc(&d, sizeof h) != cudaSuccess) return SSLSIM_E_NOMEM;
+  cudaMemset(d, 0, sizeof h);
+  cudaError_t e = sslsim_selftest_math_launch(n, seed, d, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return SSLSIM_E_CUDA;
+  if (bad_sqrt) *bad_sqrt = h[0];
+  if (bad_div) *bad_div = h[1];
+  return SSLSIM_OK;
+}
+
 int world_batch_set_lanes_per_world(struct WorldBatch *b, int lanes) {
   if (!b) return SSLSIM_E_ARG;
   if (lanes != 0 && lanes != 16 && lanes != 32) return SSLSIM_E_ARG;

@@ -52,6 +52,8 @@ cudaError_t sslsim_launch_referee(float4 *pos, float4 *vel, uint32_t *aux, int n
                                   float field_length, float field_width, cudaStream_t s);
 cudaError_t sslsim_launch_fork(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots, int src,
                                const int *dst, int n, cudaStream_t s);
+cudaError_t sslsim_selftest_math_launch(unsigned long long n, unsigned long long seed, unsigned long long *d_bad,
+                                        cudaStream_t s);
 cudaError_t sslsim_launch_reduce(const float4 *pos, const float4 *vel, const uint32_t *aux, int n_worlds,
                                  int n_robots, uint64_t world0, unsigned long long *out8, cudaStream_t s);
 #endif

@@ -526,6 +526,17 @@ def test_command_sequence_in_one_launch(sim, orc):
     _compare(b.read_state(), o, 10)
 
 
+def test_fast_math_is_correctly_rounded(sim):
+    """The kernel's branch-free sqrt / division (nvcc's fast-path sequences without the range-check stub) against
+    sqrtf and operator/ on 2^27 random operands from the ranges the kernel guarantees: bit-identical."""
+    import ctypes as C
+    bad_s, bad_d = C.c_uint64(123), C.c_uint64(123)
+    for seed in (1, 0x5351):
+        rc = sim.lib().sslsim_selftest_math(0, 1 << 26, seed, C.byref(bad_s), C.byref(bad_d))
+        assert rc == 0
+        assert bad_s.value == 0 and bad_d.value == 0, (bad_s.value, bad_d.value)
+
+
 @pytest.mark.parametrize("n_chunks", [2, 5])
 def test_chunked_pipeline_matches_whole_batch(sim, orc, n_chunks):
     """world_batch_set_chunks / chunk_step / chunk_wait: a closed loop cycling over chunks (each with its own
