@@ -1,14 +1,16 @@
 #!/bin/bash
 # A/B timing of two builds of libsslsim_b200.so in ONE gpurun session (boxes differ by a few percent, so numbers
-# from different sessions are not comparable).  A = git HEAD, B = the working tree.
+# from different sessions are not comparable).  A = git HEAD's step_kernel.cu, B = the working tree's.
 #   tools/ab_test.sh            builds both, runs them alternately on a B200 through gpurun
 set -e
 cd "$(dirname "$0")/.."
-make -s -C ssl-sim_b200/csrc clean all >/dev/null 2>&1; cp ssl-sim_b200/libsslsim_b200.so tools/_lib_B.so
-git stash -q
-make -s -C ssl-sim_b200/csrc clean all >/dev/null 2>&1; cp ssl-sim_b200/libsslsim_b200.so tools/_lib_A.so
-git stash pop -q
-make -s -C ssl-sim_b200/csrc clean all >/dev/null 2>&1
+K=ssl-sim_b200/csrc/step_kernel.cu
+make -s -C ssl-sim_b200/csrc all >/dev/null 2>&1; cp ssl-sim_b200/libsslsim_b200.so tools/_lib_B.so
+cp $K /tmp/_step_kernel_B.cu
+git show HEAD:$K > $K
+make -s -C ssl-sim_b200/csrc all >/dev/null 2>&1; cp ssl-sim_b200/libsslsim_b200.so tools/_lib_A.so
+cp /tmp/_step_kernel_B.cu $K
+make -s -C ssl-sim_b200/csrc all >/dev/null 2>&1
 cat > tools/_ab_run.sh <<'EOS'
 cp ssl-sim_b200/libsslsim_b200.so /tmp/orig.so
 for rep in 1 2; do for v in A B; do
