@@ -172,6 +172,7 @@ static StepArgs step_args(const WorldBatch *b, int first, int count, const Robot
   a.cmd = cmd ? cmd + (size_t)first * b->R : nullptr;
   a.n_worlds = count; a.n_robots = b->R; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
   a.steps_per_period = steps_per_period; a.cmd_period_stride = cmd_period_stride;
+  sslsim_step_invariants(&a, b->params);
   a.f = b->dfield; a.f_dev = b->d_field; a.p = b->params; a.prof = b->d_prof;
   return a;
 }

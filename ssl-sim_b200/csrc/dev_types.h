@@ -28,6 +28,9 @@ struct StepArgs {
   int steps_per_period;         /* > 0: command sequence, a new [W][R] block every so many steps */
   long long cmd_period_stride;  /* records between the blocks of a sequence */
   float h;
+  /* launch invariants derived from h on the host (IEEE fp32, the same values the kernel would compute): they
+   * are read as constant-bank operands instead of occupying registers for the whole launch */
+  float inv_h, gh, h_over_m, h_over_inertia, ez;
   DevField f;            /* by value: constant bank */
   const DevField *f_dev; /* the same in global memory, for the out-of-line general path */
   SslSimParams p;
@@ -35,6 +38,7 @@ struct StepArgs {
 };
 
 void sslsim_derive_field(const FieldGeometry *g, DevField *d);
+void sslsim_step_invariants(StepArgs *a, const SslSimParams &p); /* fills inv_h ... ez from a->h (step_kernel.cu) */
 
 /* kernel launchers (kernels.cu / step_kernel.cu) */
 cudaError_t sslsim_launch_step(const StepArgs &a, int lanes_per_world, cudaStream_t s);
