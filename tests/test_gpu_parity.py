@@ -526,6 +526,54 @@ def test_command_sequence_in_one_launch(sim, orc):
     _compare(b.read_state(), o, 10)
 
 
+def test_fast_math_edge_operands(sim, orc):
+    """Operands at and beyond the ranges of the kernel's branch-free sqrt / division: axis-aligned and coincident
+    contacts (zero numerators), a ball whose speed after gravity is exactly zero (sqrt(0)), lateral speeds below
+    FLT_EPSILON^(1/2) and around 1e18.5 (|l|^2 at the 1e37 guard), a ball flush against a goal wall (zero
+    components in the box direction).  Every world has to stay bit-identical to the oracle."""
+    W, R = 16, 12
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    pos, vel, aux = b.read_state()
+    pos[:, :, 2] = 0.025
+    pos[:, R, 2] = 0.0215
+    pos[:, :R, 3] = 0.0
+    for r in range(R):                                  # spread the rest far apart
+        pos[:, r, :2] = (-4.0 + 0.7 * r, 2.5)
+    pos[:, R, :2] = (0.0, -2.0)
+    vel[...] = 0.0
+    h = np.float32(1.0 / 60 / 2)
+    gh = np.float32(9.80665) * h
+    # 0: robots touching, centres aligned along x (dy == 0) / 1: along y (dx == 0) / 2: coincident centres
+    pos[0, 0, :2] = (0.0, 0.0); pos[0, 1, :2] = (0.17, 0.0)
+    pos[1, 0, :2] = (1.0, 0.0); pos[1, 1, :2] = (1.0, 0.175)
+    pos[2, 0, :2] = (2.0, 1.0); pos[2, 1, :2] = (2.0, 1.0)
+    # 3: ball against a robot with dx == 0 / 4: ball exactly above the robot axis, falling on its top
+    pos[3, R, :2] = (0.5, 0.11); pos[3, 0, :2] = (0.5, 0.0)
+    pos[4, R, :3] = (0.5, 0.0, 0.16); pos[4, 0, :2] = (0.5, 0.0)
+    # 5: ball moving up at exactly GRAV*h: zero speed after gravity, sqrt(0) in the margin
+    pos[5, R, 2] = 0.3; vel[5, R, 2] = gh
+    # 6: ball flush against the inner face of a goal side wall (dx == 0 relative to the box), 7: against the rear wall
+    pos[6, R, :2] = (4.6, 0.5 - 0.0215); vel[6, R, 1] = 0.3
+    pos[7, R, :2] = (4.68 - 0.0215, 0.2); vel[7, R, 0] = 0.3
+    # 8: robot sliding along a wall with a lateral speed below / 9: just above sqrt(FLT_EPSILON)
+    pos[8, 0, :2] = (5.2 - 0.095, 0.0); vel[8, 0, :2] = (0.5, 3.0e-4)
+    pos[9, 0, :2] = (5.2 - 0.095, 0.0); vel[9, 0, :2] = (0.5, 4.0e-4)
+    # 10 / 11: lateral speeds whose squares straddle the 1e37 guard (the worlds blow up; they must blow up identically)
+    vel[10, 0, :2] = (3.0e18, 0.0); vel[11, 0, :2] = (3.3e18, 0.0)
+    # 12: denormal-small offsets between touching robots / 13: tiny lateral velocity on the ground (l2 denormal)
+    pos[12, 0, :2] = (0.0, 0.0); pos[12, 1, :2] = (0.17, 1e-39)
+    vel[13, 0, :2] = (1e-20, 1e-21)
+    b.write_state(pos, vel, aux)
+    o.pos[...] = pos; o.vel[...] = vel
+    cmd = np.zeros((W, R), sim.CMD_DTYPE)                # passive robots: sliding friction on the ground rows
+    b.set_commands(cmd); o.cmd = cmd.copy()
+    for chunk in (1, 1, 4, 30):
+        b.step(chunk); o.step(chunk)
+        _compare(b.read_state(), o, chunk, "after %d" % chunk)
+    assert o.aux[:5, 7].min() > 0
+
+
 def test_fast_math_is_correctly_rounded(sim):
     """The kernel's branch-free sqrt / division (nvcc's fast-path sequences without the range-check stub) against
     sqrtf and operator/ on 2^27 random operands from the ranges the kernel guarantees: bit-identical."""
