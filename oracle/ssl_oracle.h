@@ -13,7 +13,10 @@
  * environment; the reference ships no tests, golden vectors or fixtures.
  * This file is therefore a plain-C restatement of the Bullet 2.82 step *as
  * exercised by the reference scene*, following docs/STEP_SPEC.md.  Every
- * scene constant cites the reference line it comes from.
+ * scene constant cites the reference line it comes from.  (What the reference
+ * can still build without Bullet -- its field geometry, src/field.c -- is
+ * compiled in place into oracle/_ref/ and pins the field constants used here:
+ * tests/test_reference_field.py.)
  *
  * One world at a time, scalar, single thread, straightforward loops.
  */

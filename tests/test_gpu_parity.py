@@ -526,6 +526,27 @@ def test_command_sequence_in_one_launch(sim, orc):
     _compare(b.read_state(), o, 10)
 
 
+def test_long_horizon_parity(sim, orc):
+    """The drift bound north_star asks for over 600 steps, taken to 9,000 world-steps (150 s of play) with kicks,
+    dribbling and wheel commands redrawn every 30 steps on 128 worlds: the CUDA path and the oracle do not drift
+    apart at all (bit-identical state, events and counters), with goals, ball-outs and thousands of touches on the way."""
+    import os
+    W, R, T = 128, 12, os.cpu_count() or 1
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    for period in range(300):
+        o.gen_commands(period, 1)
+        b.gen_commands(period, 1)
+        b.step(30)
+        o.step(30, threads=T)
+        if period % 100 == 99:
+            _compare(b.read_state(), o, 30, "period %d" % period)
+            b.referee(); o.referee()      # put out-of-play balls back so that the worlds keep playing
+    st = b.reduce_stats()
+    assert st["bad_worlds"] == 0 and st["kicks"] > 100 and st["touches"] > 1000
+    assert st["contacts"] == int(o.aux[:, 7].astype(np.uint64).sum())
+
+
 def test_fast_math_edge_operands(sim, orc):
     """Operands at and beyond the ranges of the kernel's branch-free sqrt / division: axis-aligned and coincident
     contacts (zero numerators), a ball whose speed after gravity is exactly zero (sqrt(0)), lateral speeds below
