@@ -107,6 +107,22 @@ def test_no_device_fails_loudly(sim):
         sim.World()
 
 
+def test_null_handles_are_argument_errors(sim):
+    """The batched calls return SSLSIM_E_ARG (-1) on a NULL batch instead of touching it (no GPU needed)."""
+    L = sim.lib()
+    assert L.world_batch_step(None, 1) == -1
+    assert L.world_batch_sync(None) == -1
+    assert L.world_batch_set_chunks(None, 4) == -1
+    assert L.world_batch_chunk_step(None, 0, None, 1, None) == -1
+    assert L.world_batch_chunk_wait(None, 0) == -1
+    assert L.world_batch_chunk_count(None) == 0
+    assert L.world_batch_chunk_range(None, 0, None, None) == -1
+    assert L.world_batch_read_aux(None, None) == -1
+    assert L.world_batch_world_count(None) == 0 and L.world_batch_device(None) == -1
+    assert L.world_batch_last_error(None) == -1
+    assert L.world_batch_error_string(None) == b"null batch"
+
+
 def test_product_does_not_touch_oracle():
     """Nothing under ssl-sim_b200/ or include/ may reference the oracle."""
     for base in ("ssl-sim_b200", "include"):

@@ -644,6 +644,38 @@ def test_chunked_pipeline_matches_whole_batch(sim, orc, n_chunks):
     _compare(b.read_state(), o, 10)
 
 
+def test_chunk_api_argument_errors_and_interleaving(sim, orc):
+    """Out-of-range chunks are argument errors; whole-batch calls between chunk calls are ordered after the queued
+    chunk work (and chunk work after them); switching the pipeline off and on again keeps the worlds."""
+    import ctypes as C
+    W, R = 24, 12
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(W, R)
+    L = sim.lib()
+    assert L.world_batch_chunk_step(b._h, 0, None, 1, None) == -1      # no pipeline yet
+    assert L.world_batch_set_chunks(b._h, W + 1) == -1
+    b.set_chunks(3)
+    assert L.world_batch_chunk_count(b._h) == 3
+    assert L.world_batch_chunk_step(b._h, 3, None, 1, None) == -1 and L.world_batch_chunk_wait(b._h, -1) == -1
+    o.gen_commands(0, 1)
+    for c in range(3):
+        first, count = b.chunk_range(c)
+        blk = np.ascontiguousarray(o.cmd[first:first + count])
+        b.chunk_step(c, blk.ctypes.data_as(C.c_void_p), 25, None)
+    b.step(5)                      # whole batch, installed commands: ordered after the three chunk launches
+    o.step(30)
+    for c in range(3):
+        b.chunk_step(c, None, 10, None)   # and these after the whole-batch launch
+    o.step(10)
+    _compare(b.read_state(), o, 40)      # read_state joins the chunk streams
+    b.set_chunks(0); b.step(7); o.step(7)
+    b.set_chunks(2)
+    for c in range(2):
+        b.chunk_step(c, None, 3, None)
+    o.step(3)
+    _compare(b.read_state(), o, 10)
+
+
 def test_legacy_accessors_on_batch_members(sim, orc):
     """The upstream TODO stubs (reference src/sslsim.cpp:390-428, 452-471) implemented, used on members of a
     batch through world_batch_get_world: getters mirror the device state, setters write through."""
