@@ -6,6 +6,8 @@ velocities within 1e-4 m / 1e-3 rad per step.  The kernel is compiled with --fma
 and follows the oracle's association order, so these tests additionally assert
 bit-equality of the whole state (the stated tolerance is still checked first).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -524,6 +526,55 @@ def test_command_sequence_in_one_launch(sim, orc):
     # the last block stays installed
     b.step(10); o.step(10)
     _compare(b.read_state(), o, 10)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("SSLSIM_FUZZ_SEEDS", "12"))))   # more seeds: SSLSIM_FUZZ_SEEDS=300
+def test_random_fields_tunables_and_commands(sim, orc, seed):
+    """Property test over what the fixed cases leave out: random field geometry (sizes, goal width / depth / wall
+    thickness / height), random builder tunables (kicker, dribbler, wheel model, rolling resistance, solver
+    iterations, ball model), random robot counts and lane mappings, random substep schemes, random initial velocities
+    and random commands in both command modes -- bit-identical to the oracle every time."""
+    rng = np.random.default_rng(1000 + seed)
+    f32 = lambda a, b: float(np.float32(rng.uniform(a, b)))
+    R = int(rng.choice([1, 3, 6, 12, 15, 16, 22, 31]))
+    W = int(rng.integers(5, 40))
+    fld = (0.01, f32(2.0, 12.0), f32(1.5, 9.0), f32(0.05, 0.4), f32(0.0, 0.5), f32(0.3, 1.8), f32(0.1, 0.3),
+           f32(0.01, 0.05), 0.5, 1.0, 0.5, 0.2, 1.0, 0.4, f32(0.1, 0.3))
+    if fld[5] + 2 * fld[7] + 0.3 > fld[2]:             # the goal has to fit the field width
+        fld = fld[:5] + (f32(0.3, 0.6),) + fld[6:]
+    kw = dict(flags=int(rng.integers(0, 2)), solver_iterations=int(rng.choice([1, 2, 5, 10, 13])),
+              kick_reach=f32(0.0, 0.05), kick_halfwidth=f32(0.01, 0.08), kick_max_height=f32(0.0, 0.1),
+              wheel_kp=f32(1.0, 60.0), wheel_fmax=f32(0.5, 10.0), robot_yaw_inertia=f32(0.002, 0.05),
+              dribble_kd=f32(0.0, 120.0), dribble_cd=f32(0.0, 20.0), dribble_amax=f32(0.0, 30.0),
+              dribble_reach=f32(0.0, 0.06), mu_roll=f32(0.0, 0.2))
+    b = sim.WorldBatch(W, R, fld=sim.FieldGeometry(*fld), params=sim.default_params(**kw), seed=77 + seed)
+    o = orc.Worlds(W, R, fld=fld, params=orc.default_params(**kw), seed=77 + seed)
+    if R + 1 <= 16 and rng.integers(0, 2):
+        b.set_lanes_per_world(32)
+    pos, vel, aux = b.read_state()
+    np.testing.assert_array_equal(pos, o.pos)
+    pos[:, :, 2] = np.where(rng.random((W, R + 1)) < 0.7, 0.025, pos[:, :, 2]).astype(np.float32)   # most on the ground
+    pos[:, R, 2] = np.where(rng.random(W) < 0.7, 0.0215, 0.3).astype(np.float32)
+    vel[:, :, :2] = rng.normal(0, 1.5, (W, R + 1, 2)).astype(np.float32)
+    vel[:, R, :3] = rng.normal(0, 3.0, (W, 3)).astype(np.float32)
+    vel[:, :R, 3] = rng.normal(0, 3.0, (W, R)).astype(np.float32)
+    if kw["flags"] == 0:
+        pos[:, R, 3] = 0.0; vel[:, R, 3] = 0.0        # no ball spin state in the sliding model
+    b.write_state(pos, vel, aux)
+    o.pos[...] = pos; o.vel[...] = vel
+    sub, h = [(2, 1.0 / 120), (1, 1.0 / 60), (3, 1.0 / 200), (4, 1.0 / 240)][int(rng.integers(0, 4))]
+    for period in range(4):
+        cmd = np.zeros((W, R), sim.CMD_DTYPE)
+        mode = rng.integers(0, 3, (W, R))              # passive / wheel speeds / velocity commands
+        cmd["flags"] = np.where(mode == 0, 0, np.where(mode == 1, sim.CMD_DRIVE | sim.CMD_WHEELS, sim.CMD_DRIVE))
+        cmd["flags"] |= np.where(rng.random((W, R)) < 0.4, sim.CMD_SPINNER, 0).astype(np.uint32)
+        cmd["wheel"] = np.where((mode == 1)[..., None], rng.uniform(-60, 60, (W, R, 4)), rng.uniform(-2, 2, (W, R, 4))).astype(np.float32)
+        cmd["kickspeedx"] = np.where(rng.random((W, R)) < 0.3, rng.uniform(0, 7, (W, R)), 0).astype(np.float32)
+        cmd["kickspeedz"] = np.where(rng.random((W, R)) < 0.3, rng.uniform(0, 4, (W, R)), 0).astype(np.float32)
+        b.set_commands(cmd); o.cmd = cmd.copy()
+        n = int(rng.integers(1, 40))
+        b.step_delta(n, sub, h); o.step(n, substeps=sub, h=np.float32(h))
+        _compare(b.read_state(), o, n, "seed %d period %d R=%d sub=%d" % (seed, period, R, sub))
 
 
 def test_long_horizon_parity(sim, orc):
