@@ -140,7 +140,8 @@ int world_batch_sync(struct WorldBatch *batch);
  * slowest one, and for the copies) is what limits it.  world_batch_set_chunks splits the batch into n contiguous
  * ranges of worlds, each with its own CUDA stream.  world_batch_chunk_step queues on the chunk's stream: the
  * H2D copy of the chunk's commands (host_cmds = [chunk worlds][n_robots] records, pinned memory for a truly
- * asynchronous copy; NULL keeps the installed ones), n_steps world-steps of the chunk's worlds, and the D2H copy
+ * asynchronous copy; NULL keeps what the batch's command buffer holds for the chunk -- passive robots until
+ * the chunk was given commands), n_steps world-steps of the chunk's worlds, and the D2H copy
  * of their aux words into host_aux ([chunk worlds][8], may be NULL) -- and returns at once.
  * world_batch_chunk_wait blocks until that work is done and host_aux is valid.  A closed-loop caller cycles
  * over the chunks (wait c, decide, submit c): copies, launches and the tail of each launch overlap with the

@@ -304,7 +304,11 @@ int world_batch_set_chunks(struct WorldBatch *b, int n_chunks) {
   free_chunks(b);
   if (n_chunks <= 1) return SSLSIM_OK;
   if (!b->ev_main) CK(cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming));
-  if (!b->d_cmd && b->R > 0) CK(cudaMalloc(&b->d_cmd, (size_t)b->W * b->R * sizeof(RobotCommand)));
+  if (!b->d_cmd && b->R > 0) {
+    CK(cudaMalloc(&b->d_cmd, (size_t)b->W * b->R * sizeof(RobotCommand)));
+    /* zeroed = passive robots: a chunk that is stepped before it was ever given commands must not read garbage */
+    CK(cudaMemsetAsync(b->d_cmd, 0, (size_t)b->W * b->R * sizeof(RobotCommand), b->stream));
+  }
   b->chunks.resize(n_chunks);
   for (int c = 0; c < n_chunks; ++c) {
     WorldBatch::Chunk &k = b->chunks[c];
@@ -361,7 +365,10 @@ int world_batch_chunk_wait(struct WorldBatch *b, int chunk) {
 }
 
 static int ensure_cmd_buffer(WorldBatch *b) {
-  if (!b->d_cmd && b->R > 0) CK(cudaMalloc(&b->d_cmd, (size_t)b->W * b->R * sizeof(RobotCommand)));
+  if (!b->d_cmd && b->R > 0) {
+    CK(cudaMalloc(&b->d_cmd, (size_t)b->W * b->R * sizeof(RobotCommand)));
+    CK(cudaMemsetAsync(b->d_cmd, 0, (size_t)b->W * b->R * sizeof(RobotCommand), b->stream)); /* passive robots */
+  }
   return SSLSIM_OK;
 }
 
