@@ -1,3 +1,7 @@
+# The measurement suite behind profiles/r1_v14_*: run on a B200 with
+#   gpurun --timeout 1500 -- 'bash tools/measure_suite.sh'
+# then `python tools/make_profile_summary.py r1_v14 gpurun_out/prof_v14.ncu-rep gpurun_out/launches_v14.csv
+# gpurun_out/bench_v14.json 1228800` here.  Every ncu pass runs only after the same command exited 0 without ncu.
 set -x
 python bench.py > gpurun_out/bench_v14.json 2> gpurun_out/bench_v14.err || exit 1
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_v14_ref.json 2>> gpurun_out/bench_v14.err
