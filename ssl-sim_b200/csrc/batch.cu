@@ -22,33 +22,6 @@ const struct FieldGeometry FIELD_DIV_A = {0.010f, 12.0f, 9.0f, 0.30f, 0.40f, 1.8
                                           0.5f, 1.0f, 0.5f, 0.2f, 1.0f, 0.4f, 0.16f};
 }
 
-/* planes and goal boxes of the reference scene (src/sslsim.cpp:145-203, src/field.h:36-42) */
-void sslsim_derive_field(const FieldGeometry *f, DevField *d) {
-  d->half_len = f->field_length / 2;
-  d->half_wid = f->field_width / 2;
-  d->limit_x = f->field_length / 2 + f->boundary_width + f->referee_width;
-  d->limit_y = f->field_width / 2 + f->boundary_width + f->referee_width;
-  d->goal_half_w = f->goal_width / 2;
-  d->goal_back = d->half_len + f->goal_depth;
-  d->goal_height = f->goal_height;
-  d->goal_reach_y = f->goal_width / 2 + f->goal_wall_width;
-  d->goal_reach_x = f->field_length / 2 + f->goal_depth + f->goal_wall_width;
-  const float ww = f->goal_wall_width, gd = f->goal_depth, gw = f->goal_width, gh = f->goal_height;
-  const float sx = -d->half_len + (-gd / 2 - ww / 2), shx = gd / 2 + ww / 2;
-  const float sy = gw / 2 + ww / 2, shy = ww / 2;
-  const float rx = -d->half_len + (-gd - ww / 2), rhx = ww / 2, rhy = gw / 2;
-  const float cz = gh / 2, hz = gh / 2;
-  d->lo[0][0] = sx - shx; d->hi[0][0] = sx + shx; d->lo[0][1] = -sy - shy; d->hi[0][1] = -sy + shy;
-  d->lo[1][0] = sx - shx; d->hi[1][0] = sx + shx; d->lo[1][1] = sy - shy;  d->hi[1][1] = sy + shy;
-  d->lo[2][0] = rx - rhx; d->hi[2][0] = rx + rhx; d->lo[2][1] = -rhy;      d->hi[2][1] = rhy;
-  for (int k = 0; k < 3; k++) { d->lo[k][2] = cz - hz; d->hi[k][2] = cz + hz; }
-  for (int k = 0; k < 3; k++) {
-    d->lo[3 + k][0] = -d->hi[k][0]; d->hi[3 + k][0] = -d->lo[k][0];
-    d->lo[3 + k][1] = -d->hi[k][1]; d->hi[3 + k][1] = -d->lo[k][1];
-    d->lo[3 + k][2] = d->lo[k][2];  d->hi[3 + k][2] = d->hi[k][2];
-  }
-}
-
 bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what) {
   if (e == cudaSuccess) return true;
   if (b) {
