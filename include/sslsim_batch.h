@@ -46,7 +46,9 @@ struct SslSimParams {
   float wheel_kp, wheel_fmax, robot_yaw_inertia;
   float dribble_kd, dribble_cd, dribble_amax, dribble_reach;
   float mu_roll;
-  float reserved[3];
+  float restitution_threshold; /* Bullet's m_restitutionVelocityThreshold: 0 = Bullet 2.82 (no threshold, the default
+                                  here); 0.2 = btContactSolverInfo's default from Bullet 2.87 on */
+  float reserved[2];
 };
 #define SSLSIM_F_BALL_SPIN 1u /* ball rolls (spin state + rolling resistance) instead of the reference's pure sliding */
 void sslsim_params_default(struct SslSimParams *p);
@@ -76,7 +78,10 @@ enum {
   SSLSIM_AUX_STATUS = 0,  /* [7:0] last touching robot index (0xFF none); bit8/9/10 ball currently in +x goal /
                              -x goal / out; bits 12..15 events of the last step: goal for blue (+x goal),
                              goal for yellow (-x goal), ball out, kicked; bit16 contact-row overflow (sticky);
-                             bit17 non-finite state (sticky) */
+                             bit17 non-finite state (sticky); bits 18..19 ball activation state (Bullet's
+                             ACTIVE_TAG = 0 / WANTS_DEACTIVATION = 1 / ISLAND_SLEEPING = 2; the reference's ball may
+                             sleep, src/sslsim.cpp:51-61, its robots may not, :113); bits 20..31 consecutive
+                             substeps with the ball below the sleeping thresholds (saturating) */
   SSLSIM_AUX_PEAK2 = 1,   /* f32 bits: peak |v_ball|^2 since the last kick */
   SSLSIM_AUX_TOUCH = 2,   /* robots that touched the ball during the last step (bit i = robot i) */
   SSLSIM_AUX_RESTARTS = 3, /* restarts placed by world_batch_referee */

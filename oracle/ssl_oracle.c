@@ -12,9 +12,11 @@
  * internalSingleStepSimulation), restated from their published algorithm.
  *
  * Build: gcc -O2 -ffp-contract=off (no fast-math).  All arithmetic is IEEE
- * binary32 with the association order written here; the CUDA kernel is
- * compiled with --fmad=false and follows the same order, so the two agree
- * bit-for-bit in practice (tests still state a tolerance).
+ * binary32 with the association order written here.  The compiler contracts
+ * nothing; where STEP_SPEC section 0 says fused multiply-add the code calls
+ * fmaf() (through mad / nmad / dot2 / dot3 below), and the CUDA kernel, compiled
+ * with --fmad=false, calls __fmaf_rn at the same places, so the two agree
+ * bit-for-bit ("FMA in both via fmaf").
  */
 #include "ssl_oracle.h"
 #include <math.h>
@@ -44,7 +46,12 @@
 #define ERP 0.2f
 #define ERP2 0.8f
 #define SPLIT_THRESH (-0.04f)
-#define REST_THRESH 0.2f      /* restitution velocity threshold (Bullet >= 2.87 default) */
+#define SLEEP_LIN2 0.64f      /* btRigidBody default linear sleeping threshold 0.8, squared */
+#define SLEEP_ANG2 1.0f       /* default angular sleeping threshold 1.0, squared */
+#define SLEEP_TIME 2.0f       /* gDeactivationTime */
+/* reach of a robot's collision shapes from its axis: chassis radius + the wheel cylinders that stick out of it
+ * (reference :81-98: wheel centres at ROBOT_DIAM/2 + WHEEL_WIDTH/2, half width WHEEL_WIDTH/2) */
+#define ROBOT_REACH 0.1f
 #define FLT_EPS 1.1920929e-07f
 #define L2_MAX 1e37f /* squared lateral speed above which the direction falls back like a zero one (overflow guard) */
 #define TWO_PI 6.2831855f
@@ -54,6 +61,14 @@ static const float WCOS[4] = {0.5f, -0.70710677f, -0.70710677f, 0.5f};
 
 #define MAX_SERIAL_ROWS 64
 #define MAX_BODY_STATICS 4
+
+/* STEP_SPEC section 0: the four fused forms; everything else is one rounding per operator */
+static inline float mad(float a, float b, float c) { return fmaf(a, b, c); }   /* a*b + c */
+static inline float nmad(float a, float b, float c) { return fmaf(-a, b, c); } /* c - a*b */
+static inline float dot2(float ax, float ay, float bx, float by) { return fmaf(ay, by, ax * bx); }
+static inline float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return fmaf(az, bz, fmaf(ay, by, ax * bx));
+}
 
 void orc_params_default(orc_params *p) {
   memset(p, 0, sizeof *p);
@@ -70,6 +85,7 @@ void orc_params_default(orc_params *p) {
   p->dribble_amax = 12.0f;
   p->dribble_reach = 0.03f;
   p->mu_roll = 0.03f;
+  p->restitution_threshold = 0.0f; /* Bullet 2.82: none (0.2 is btContactSolverInfo's default from 2.87 on) */
 }
 
 /* ---- counter RNG --------------------------------------------------------- */
@@ -91,16 +107,16 @@ float orc_u01(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
 void orc_sincos(float x, float *s, float *c) {
   float kf = rintf(x * 0.63661975f);
   int k = (int)kf;
-  float r = x - kf * 1.5703125f;
-  r = r - kf * 4.837512969970703125e-4f;
-  r = r - kf * 7.54978995489188216e-8f;
+  float r = nmad(kf, 1.5703125f, x);
+  r = nmad(kf, 4.837512969970703125e-4f, r);
+  r = nmad(kf, 7.54978995489188216e-8f, r);
   float z = r * r;
-  float sp = -1.9515295891e-4f * z + 8.3321608736e-3f;
-  sp = sp * z - 1.6666654611e-1f;
-  sp = sp * z * r + r;
-  float cp = 2.443315711809948e-5f * z - 1.388731625493765e-3f;
-  cp = cp * z + 4.166664568298827e-2f;
-  cp = cp * z * z - 0.5f * z + 1.0f;
+  float sp = mad(-1.9515295891e-4f, z, 8.3321608736e-3f);
+  sp = mad(sp, z, -1.6666654611e-1f);
+  sp = mad(sp * z, r, r);
+  float cp = mad(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+  cp = mad(cp, z, 4.166664568298827e-2f);
+  cp = mad(cp * z, z, mad(-0.5f, z, 1.0f));
   switch (k & 3) {
   case 0: *s = sp; *c = cp; break;
   case 1: *s = cp; *c = -sp; break;
@@ -158,11 +174,11 @@ static float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi 
 /* btPlaneSpace1: first tangent of the plane orthogonal to n */
 static void plane_space1(float nx, float ny, float nz, float *tx, float *ty, float *tz) {
   if (fabsf(nz) > 0.70710677f) {
-    float a = ny * ny + nz * nz;
+    float a = dot2(ny, nz, ny, nz);
     float k = 1.0f / sqrtf(a);
     *tx = 0.0f; *ty = -nz * k; *tz = ny * k;
   } else {
-    float a = nx * nx + ny * ny;
+    float a = dot2(nx, ny, nx, ny);
     float k = 1.0f / sqrtf(a);
     *tx = -ny * k; *ty = nx * k; *tz = 0.0f;
   }
@@ -175,6 +191,7 @@ typedef struct {
   const float *hvx, *hvy, *hvz; /* vel + external impulses */
   int spin_mode;
   float ball_margin;
+  float rest_thresh;
   const uint32_t *cflags;    /* per robot command flags or NULL */
 } gen_ctx;
 
@@ -185,27 +202,27 @@ static void finish_row(const gen_ctx *g, row_t *r, float nx, float ny, float nz,
   r->acc_n = r->acc_f = r->acc_p = 0.0f;
   float rvx = g->vel[a].x, rvy = g->vel[a].y, rvz = g->vel[a].z;
   if (b >= 0) { rvx = rvx - g->vel[b].x; rvy = rvy - g->vel[b].y; rvz = rvz - g->vel[b].z; }
-  float vn = nx * rvx + ny * rvy + nz * rvz;
-  float rest = (-vn > REST_THRESH) ? e * (-vn) : 0.0f;
+  float vn = dot3(nx, ny, nz, rvx, rvy, rvz);
+  float rest = (-vn > g->rest_thresh) ? e * (-vn) : 0.0f;
   float push = 0.0f;
   if (dist > 0.0f) {
     /* speculative row: the gap may close but not overshoot; if it closes within
      * this substep and the pair is restitutive, reflect now (STEP_SPEC 4.3) */
     float hx = g->hvx[a], hy = g->hvy[a], hz = g->hvz[a];
     if (b >= 0) { hx = hx - g->hvx[b]; hy = hy - g->hvy[b]; hz = hz - g->hvz[b]; }
-    float hn = nx * hx + ny * hy + nz * hz;
-    int closing = (hn * g->h + dist) < 0.0f;
+    float hn = dot3(nx, ny, nz, hx, hy, hz);
+    int closing = mad(hn, g->h, dist) < 0.0f;
     r->target = (closing && rest > 0.0f) ? rest : -(dist * g->inv_h);
   } else if (dist > SPLIT_THRESH) {
-    r->target = rest + -(dist * ERP) * g->inv_h;
+    r->target = mad(-(dist * ERP), g->inv_h, rest);
   } else {
     r->target = rest;
     push = -(dist * ERP2) * g->inv_h;
   }
   r->push_target = push;
   /* single friction direction along the lateral relative velocity */
-  float lx = rvx - nx * vn, ly = rvy - ny * vn, lz = rvz - nz * vn;
-  float l2 = lx * lx + ly * ly + lz * lz;
+  float lx = nmad(nx, vn, rvx), ly = nmad(ny, vn, rvy), lz = nmad(nz, vn, rvz);
+  float l2 = dot3(lx, ly, lz, lx, ly, lz);
   if (l2 > FLT_EPS && l2 < L2_MAX) {
     float k = 1.0f / sqrtf(l2);
     r->tx = lx * k; r->ty = ly * k; r->tz = lz * k;
@@ -228,9 +245,9 @@ static int gen_ground(const gen_ctx *g, int b, row_t *r) {
   finish_row(g, r, 0.0f, 0.0f, 1.0f, dist, b, -1, ball ? E_BALL_PLANE : E_ROBOT_PLANE, mu);
   if (ball && g->spin_mode) {
     /* friction direction from the contact-point velocity (v + w x r_c), r_c = (0,0,-r) */
-    float cvx = g->vel[b].x - BALL_R * g->vel[b].w; /* vel.w = omega_y */
-    float cvy = g->vel[b].y + BALL_R * g->pos[b].w; /* pos.w = omega_x */
-    float l2 = cvx * cvx + cvy * cvy;
+    float cvx = nmad(BALL_R, g->vel[b].w, g->vel[b].x); /* vel.w = omega_y */
+    float cvy = mad(BALL_R, g->pos[b].w, g->vel[b].y);  /* pos.w = omega_x */
+    float l2 = dot2(cvx, cvy, cvx, cvy);
     if (l2 > FLT_EPS && l2 < L2_MAX) {
       float k = 1.0f / sqrtf(l2);
       r->tx = cvx * k; r->ty = cvy * k; r->tz = 0.0f;
@@ -273,7 +290,7 @@ static int gen_statics(const gen_ctx *g, const field_derived *d, int b, row_t *o
     if (ball) {
       float cx = clampf(px, lo[0], hi[0]), cy = clampf(py, lo[1], hi[1]), cz = clampf(pz, lo[2], hi[2]);
       float dx = px - cx, dy = py - cy, dz = pz - cz;
-      float d2 = dx * dx + dy * dy + dz * dz;
+      float d2 = dot3(dx, dy, dz, dx, dy, dz);
       if (d2 > 0.0f) {
         float dd = sqrtf(d2);
         nx = dx / dd; ny = dy / dd; nz = dz / dd;
@@ -290,7 +307,7 @@ static int gen_statics(const gen_ctx *g, const field_derived *d, int b, row_t *o
     } else {
       float cx = clampf(px, lo[0], hi[0]), cy = clampf(py, lo[1], hi[1]);
       float dx = px - cx, dy = py - cy;
-      float d2 = dx * dx + dy * dy;
+      float d2 = dot2(dx, dy, dx, dy);
       float hx, hy, sh;
       if (d2 > 0.0f) {
         float dd = sqrtf(d2);
@@ -318,7 +335,7 @@ static int gen_statics(const gen_ctx *g, const field_derived *d, int b, row_t *o
 /* robot i vs robot j (i < j): parallel capped cylinders; normal points j -> i */
 static int gen_robot_robot(const gen_ctx *g, int i, int j, row_t *r) {
   float dx = g->pos[i].x - g->pos[j].x, dy = g->pos[i].y - g->pos[j].y;
-  float d2 = dx * dx + dy * dy;
+  float d2 = dot2(dx, dy, dx, dy);
   float lim = 2.0f * ROBOT_R + MARGIN;
   if (!(d2 <= lim * lim)) return 0;
   float dd = sqrtf(d2);
@@ -341,7 +358,7 @@ static int gen_robot_robot(const gen_ctx *g, int i, int j, row_t *r) {
 static int gen_ball_robot(const gen_ctx *g, int i, row_t *r) {
   int B = g->R;
   float dx = g->pos[B].x - g->pos[i].x, dy = g->pos[B].y - g->pos[i].y;
-  float d2 = dx * dx + dy * dy;
+  float d2 = dot2(dx, dy, dx, dy);
   float lim = ROBOT_R + BALL_R + g->ball_margin;
   if (!(d2 <= lim * lim)) return 0;
   float dd = sqrtf(d2);
@@ -354,7 +371,7 @@ static int gen_ball_robot(const gen_ctx *g, int i, row_t *r) {
   float sg = s_hi >= s_lo ? 1.0f : -1.0f;
   float nx, ny, nz, dist;
   if (sh > 0.0f && sv > 0.0f) {
-    float ee = sqrtf(sh * sh + sv * sv);
+    float ee = sqrtf(dot2(sh, sv, sh, sv));
     float kh = sh / ee, kv = sv / ee;
     nx = hx * kh; ny = hy * kh; nz = sg * kv;
     dist = ee - BALL_R;
@@ -365,15 +382,56 @@ static int gen_ball_robot(const gen_ctx *g, int i, row_t *r) {
   return 1;
 }
 
+/* ---- ball activation state (Bullet btCollisionObject activation states; robots are DISABLE_DEACTIVATION,
+ * reference :113, the ball is not, :51-61).  Kept in the status word: bits 18-19 the state, bits 20-31 the
+ * number of consecutive slow substeps (Bullet's m_deactivationTime is that many additions of h in binary32, so
+ * the count determines it exactly; orc_sleep_substeps gives the count at which it first exceeds 2 s). ------ */
+#define ACT_SHIFT 18
+#define ACT_ACTIVE 0u  /* ACTIVE_TAG */
+#define ACT_WANTS 1u   /* WANTS_DEACTIVATION */
+#define ACT_ASLEEP 2u  /* ISLAND_SLEEPING */
+#define CNT_SHIFT 20
+#define CNT_MAX 4095u
+
+int orc_sleep_substeps(float h) {
+  float t = 0.0f;
+  for (int n = 1; n <= (int)CNT_MAX; n++) {
+    t = t + h;                       /* m_deactivationTime += timeStep */
+    if (t > SLEEP_TIME) return n;    /* wantsSleeping(): m_deactivationTime > gDeactivationTime */
+  }
+  return (int)CNT_MAX + 1;           /* never within the counter's range (h < 0.5 ms): the ball stays awake */
+}
+
 /* ---- one substep (Bullet internalSingleStepSimulation, STEP_SPEC 4) ------- */
 static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4 *pos,
-                    orc_vec4 *vel, uint32_t *aux, const orc_cmd *cmd, float h) {
+                    orc_vec4 *vel, uint32_t *aux, const orc_cmd *cmd, float h, int ball_gravity,
+                    int sleep_substeps) {
   const int N = R + 1, B = R;
   const float inv_h = 1.0f / h;
   const int spin_mode = (p->flags & ORC_F_BALL_SPIN) != 0;
   float ex[ORC_MAX_BODIES], ey[ORC_MAX_BODIES], ez[ORC_MAX_BODIES], ew[ORC_MAX_BODIES];
   uint32_t cflags[ORC_MAX_BODIES];
   for (int b = 0; b < N; b++) { ex[b] = ey[b] = ez[b] = ew[b] = 0.0f; cflags[b] = 0; }
+
+  /* 4.0 simulation islands (Bullet btSimulationIslandManager::buildIslands, restated for a scene whose only
+   * body that may sleep is the ball): the ball shares an island with a robot iff their broadphase boxes overlap
+   * -- closed form [DEV]: horizontal distance of the ball centre from the robot axis <= ROBOT_REACH + BALL_R +
+   * 2 margins (each shape grown by the contact breaking threshold).  An island with a robot never sleeps and
+   * wakes a sleeping ball (ISLAND_SLEEPING -> WANTS_DEACTIVATION, time 0); a ball alone sleeps as soon as it
+   * wants to. */
+  uint32_t act = (aux[ORC_AUX_STATUS] >> ACT_SHIFT) & 3u, cnt = aux[ORC_AUX_STATUS] >> CNT_SHIFT;
+  if (act != ACT_ACTIVE) {
+    int near = 0;
+    const float lim = ROBOT_REACH + BALL_R + 2.0f * MARGIN;
+    for (int r = 0; r < R; r++) {
+      float dx = pos[B].x - pos[r].x, dy = pos[B].y - pos[r].y;
+      float d2 = dot2(dx, dy, dx, dy);
+      near |= d2 <= lim * lim;
+    }
+    if (near) { if (act == ACT_ASLEEP) { act = ACT_WANTS; cnt = 0; } }
+    else act = ACT_ASLEEP;
+  }
+  const int asleep = act == ACT_ASLEEP; /* not solved, not integrated (btRigidBody::isActive() is false) */
 
   /* 4.1 actuation (new functionality; command schema reference protos/grSim_Commands.proto) */
   if (cmd) {
@@ -387,24 +445,24 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
       float s, co;
       orc_sincos(pos[r].w, &s, &co);
       float dx = bx - pos[r].x, dy = by - pos[r].y;
-      float fwd = co * dx + s * dy;
-      float lat = co * dy - s * dx;
+      float fwd = dot2(co, s, dx, dy);
+      float lat = nmad(s, dx, co * dy);
       int grounded = (pos[r].z - WHEEL_R) <= 0.005f;
       int low = (bz - BALL_R) <= p->kick_max_height;
       int in_lat = fabsf(lat) <= p->kick_halfwidth;
       if (grounded && low && in_lat && fwd > 0.0f) {
         if (c->kickspeedx > 0.0f && fwd <= ROBOT_R + BALL_R + p->kick_reach) {
           kicker = r; /* highest index wins */
-          kvx = vel[r].x + co * c->kickspeedx;
-          kvy = vel[r].y + s * c->kickspeedx;
+          kvx = mad(co, c->kickspeedx, vel[r].x);
+          kvy = mad(s, c->kickspeedx, vel[r].y);
           kvz = c->kickspeedz;
         }
         if ((c->flags & ORC_CMD_SPINNER) && fwd <= ROBOT_R + BALL_R + p->dribble_reach) {
           dribbler = r;
-          float tx = pos[r].x + (ROBOT_R + BALL_R) * co, ty = pos[r].y + (ROBOT_R + BALL_R) * s;
-          float ax = p->dribble_kd * (tx - bx) + p->dribble_cd * (vel[r].x - bvx);
-          float ay = p->dribble_kd * (ty - by) + p->dribble_cd * (vel[r].y - bvy);
-          float a2 = ax * ax + ay * ay;
+          float tx = mad(ROBOT_R + BALL_R, co, pos[r].x), ty = mad(ROBOT_R + BALL_R, s, pos[r].y);
+          float ax = mad(p->dribble_cd, vel[r].x - bvx, p->dribble_kd * (tx - bx));
+          float ay = mad(p->dribble_cd, vel[r].y - bvy, p->dribble_kd * (ty - by));
+          float a2 = dot2(ax, ay, ax, ay);
           if (a2 > p->dribble_amax * p->dribble_amax) {
             float k = p->dribble_amax / sqrtf(a2);
             ax = ax * k; ay = ay * k;
@@ -418,36 +476,39 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
           for (int i = 0; i < 4; i++) u[i] = c->wheel[i] * WHEEL_R;
         } else {
           for (int i = 0; i < 4; i++)
-            u[i] = (WCOS[i] * c->wheel[1] - WSIN[i] * c->wheel[0]) + WHEEL_RC * c->wheel[2];
+            u[i] = mad(WHEEL_RC, c->wheel[2], nmad(WSIN[i], c->wheel[0], WCOS[i] * c->wheel[1]));
         }
-        float vf = co * vel[r].x + s * vel[r].y;
-        float vl = co * vel[r].y - s * vel[r].x;
+        float vf = dot2(co, s, vel[r].x, vel[r].y);
+        float vl = nmad(s, vel[r].x, co * vel[r].y);
         float ff = 0.0f, fl = 0.0f, tq = 0.0f;
         for (int i = 0; i < 4; i++) {
-          float act = (WCOS[i] * vl - WSIN[i] * vf) + WHEEL_RC * vel[r].w;
-          float fi = clampf(p->wheel_kp * (u[i] - act), -p->wheel_fmax, p->wheel_fmax);
-          ff = ff - WSIN[i] * fi;
-          fl = fl + WCOS[i] * fi;
+          float act_i = mad(WHEEL_RC, vel[r].w, nmad(WSIN[i], vf, WCOS[i] * vl));
+          float fi = clampf(p->wheel_kp * (u[i] - act_i), -p->wheel_fmax, p->wheel_fmax);
+          ff = nmad(WSIN[i], fi, ff);
+          fl = mad(WCOS[i], fi, fl);
           tq = tq + fi;
         }
         float k = h / ROBOT_M;
-        ex[r] = (co * ff - s * fl) * k;
-        ey[r] = (s * ff + co * fl) * k;
+        ex[r] = nmad(s, fl, co * ff) * k;
+        ey[r] = mad(co, fl, s * ff) * k;
         ew[r] = (WHEEL_RC * tq) * (h / p->robot_yaw_inertia);
       }
     }
+    /* (the capture boxes lie inside the island box of 4.0, so a kicked or dribbled ball is never asleep) */
     if (kicker >= 0) {
       vel[B].x = kvx; vel[B].y = kvy; vel[B].z = kvz;
-      float s2 = kvx * kvx + kvy * kvy + kvz * kvz;
+      float s2 = dot3(kvx, kvy, kvz, kvx, kvy, kvz);
       memcpy(&aux[ORC_AUX_PEAK2], &s2, 4);
       aux[ORC_AUX_STATUS] = (aux[ORC_AUX_STATUS] & ~0xFFu) | (uint32_t)kicker | (1u << 15);
       aux[ORC_AUX_OUTS] += 1u << 16;
     }
     if (dribbler >= 0 && kicker < 0) { ex[B] = dax * h; ey[B] = day * h; }
   }
-  /* 4.2 gravity as an external impulse (Bullet: totalForce * invMass * h) */
+  /* 4.2 gravity as an external impulse (Bullet: totalForce * invMass * h).  applyGravity runs once per
+   * stepSimulation and skips a body that is asleep at that moment: ball_gravity is latched by orc_step. */
   const float gh = GRAV * h;
-  for (int b = 0; b < N; b++) ez[b] = ez[b] - gh;
+  for (int b = 0; b < N; b++) if (b != B || ball_gravity) ez[b] = ez[b] - gh;
+  if (asleep) { ex[B] = 0.0f; ey[B] = 0.0f; ez[B] = 0.0f; }
 
   /* solver velocities start at v + external impulse */
   float vx[ORC_MAX_BODIES], vy[ORC_MAX_BODIES], vz[ORC_MAX_BODIES];
@@ -464,9 +525,10 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   g.n = N; g.R = R; g.h = h; g.inv_h = inv_h; g.pos = pos; g.vel = vel; g.spin_mode = spin_mode;
   g.cflags = cmd ? cflags : 0;
   g.hvx = vx; g.hvy = vy; g.hvz = vz;
+  g.rest_thresh = p->restitution_threshold;
   {
-    float s2 = vx[B] * vx[B] + vy[B] * vy[B] + vz[B] * vz[B];
-    g.ball_margin = MARGIN + h * sqrtf(s2); /* stands in for Bullet's predictive (CCD) contact */
+    float s2 = dot3(vx[B], vy[B], vz[B], vx[B], vy[B], vz[B]);
+    g.ball_margin = asleep ? MARGIN : mad(h, sqrtf(s2), MARGIN); /* stands in for Bullet's predictive (CCD) contact */
   }
   row_t rows[MAX_SERIAL_ROWS];
   row_t ground[ORC_MAX_BODIES];
@@ -485,12 +547,16 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   for (int b = 0; b < N; b++) {
     /* at most MAX_BODY_STATICS wall/goal rows per body, first ones in canonical order (STEP_SPEC 4.3) */
     row_t tmp[MAX_BODY_STATICS];
+    if (b == B && asleep) continue; /* a sleeping ball's manifolds are not handed to the solver */
     int c = gen_statics(&g, d, b, tmp, MAX_BODY_STATICS);
     if (c > MAX_BODY_STATICS) { overflow = 1; c = MAX_BODY_STATICS; }
     for (int k = 0; k < c; k++) { if (nrows < cap) rows[nrows++] = tmp[k]; else overflow = 1; }
   }
   int nground = 0;
-  for (int b = 0; b < N; b++) { has_ground[b] = gen_ground(&g, b, &ground[b]); nground += has_ground[b]; }
+  for (int b = 0; b < N; b++) {
+    has_ground[b] = (b == B && asleep) ? 0 : gen_ground(&g, b, &ground[b]);
+    nground += has_ground[b];
+  }
   if (overflow) aux[ORC_AUX_STATUS] |= 1u << 16;
   aux[ORC_AUX_CONTACTS] += (uint32_t)(nrows + nground);
 
@@ -510,16 +576,16 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
         float meff = 1.0f / (ima + imb);
         float rx = qx[a], ry = qy[a], rz = qz[a];
         if (b >= 0) { rx = rx - qx[b]; ry = ry - qy[b]; rz = rz - qz[b]; }
-        float vn = r->nx * rx + r->ny * ry + r->nz * rz;
+        float vn = dot3(r->nx, r->ny, r->nz, rx, ry, rz);
         float dl = (r->push_target - vn) * meff;
         float sum = r->acc_p + dl;
         if (sum < 0.0f) { dl = -r->acc_p; sum = 0.0f; }
         r->acc_p = sum;
         float ka = dl * ima;
-        qx[a] = qx[a] + r->nx * ka; qy[a] = qy[a] + r->ny * ka; qz[a] = qz[a] + r->nz * ka;
+        qx[a] = mad(r->nx, ka, qx[a]); qy[a] = mad(r->ny, ka, qy[a]); qz[a] = mad(r->nz, ka, qz[a]);
         if (b >= 0) {
           float kb = dl * imb;
-          qx[b] = qx[b] - r->nx * kb; qy[b] = qy[b] - r->ny * kb; qz[b] = qz[b] - r->nz * kb;
+          qx[b] = nmad(r->nx, kb, qx[b]); qy[b] = nmad(r->ny, kb, qy[b]); qz[b] = nmad(r->nz, kb, qz[b]);
         }
       }
     }
@@ -541,16 +607,16 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
       float meff = 1.0f / (ima + imb);
       float rx = vx[a], ry = vy[a], rz = vz[a];
       if (b >= 0) { rx = rx - vx[b]; ry = ry - vy[b]; rz = rz - vz[b]; }
-      float vn = r->nx * rx + r->ny * ry + r->nz * rz;
+      float vn = dot3(r->nx, r->ny, r->nz, rx, ry, rz);
       float dl = (r->target - vn) * meff;
       float sum = r->acc_n + dl;
       if (sum < 0.0f) { dl = -r->acc_n; sum = 0.0f; }
       r->acc_n = sum;
       float ka = dl * ima;
-      vx[a] = vx[a] + r->nx * ka; vy[a] = vy[a] + r->ny * ka; vz[a] = vz[a] + r->nz * ka;
+      vx[a] = mad(r->nx, ka, vx[a]); vy[a] = mad(r->ny, ka, vy[a]); vz[a] = mad(r->nz, ka, vz[a]);
       if (b >= 0) {
         float kb = dl * imb;
-        vx[b] = vx[b] - r->nx * kb; vy[b] = vy[b] - r->ny * kb; vz[b] = vz[b] - r->nz * kb;
+        vx[b] = nmad(r->nx, kb, vx[b]); vy[b] = nmad(r->ny, kb, vy[b]); vz[b] = nmad(r->nz, kb, vz[b]);
       }
     }
     for (int k = 0; k < nrows + N; k++) {
@@ -564,13 +630,13 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
       if (b >= 0) { rx = rx - vx[b]; ry = ry - vy[b]; rz = rz - vz[b]; }
       float meff;
       if (r->spin) {
-        rx = rx - BALL_R * wy;
-        ry = ry + BALL_R * wx;
+        rx = nmad(BALL_R, wy, rx);
+        ry = mad(BALL_R, wx, ry);
         meff = spin_meff;
       } else {
         meff = 1.0f / (ima + imb);
       }
-      float vt = r->tx * rx + r->ty * ry + r->tz * rz;
+      float vt = dot3(r->tx, r->ty, r->tz, rx, ry, rz);
       float dl = (0.0f - vt) * meff;
       float lim = r->mu * r->acc_n;
       float sum = r->acc_f + dl;
@@ -578,15 +644,15 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
       else if (sum < -lim) { dl = -lim - r->acc_f; sum = -lim; }
       r->acc_f = sum;
       float ka = dl * ima;
-      vx[a] = vx[a] + r->tx * ka; vy[a] = vy[a] + r->ty * ka; vz[a] = vz[a] + r->tz * ka;
+      vx[a] = mad(r->tx, ka, vx[a]); vy[a] = mad(r->ty, ka, vy[a]); vz[a] = mad(r->tz, ka, vz[a]);
       if (b >= 0) {
         float kb = dl * imb;
-        vx[b] = vx[b] - r->tx * kb; vy[b] = vy[b] - r->ty * kb; vz[b] = vz[b] - r->tz * kb;
+        vx[b] = nmad(r->tx, kb, vx[b]); vy[b] = nmad(r->ty, kb, vy[b]); vz[b] = nmad(r->tz, kb, vz[b]);
       }
       if (r->spin) {
         float kw = dl * spin_gain;
-        wx = wx + r->ty * kw;
-        wy = wy - r->tx * kw;
+        wx = mad(r->ty, kw, wx);
+        wy = nmad(r->tx, kw, wy);
       }
     }
   }
@@ -599,7 +665,7 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   if (last >= 0) aux[ORC_AUX_STATUS] = (aux[ORC_AUX_STATUS] & ~0xFFu) | (uint32_t)last;
   aux[ORC_AUX_TOUCH] |= touch;
   if (spin_mode && has_ground[B] && ground[B].acc_n > 0.0f) {
-    float s2 = vx[B] * vx[B] + vy[B] * vy[B];
+    float s2 = dot2(vx[B], vy[B], vx[B], vy[B]);
     if (s2 > 0.0f) {
       float sp = sqrtf(s2);
       float dec = (p->mu_roll * GRAV) * h;
@@ -608,28 +674,44 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
     }
   }
   {
-    float s2 = vx[B] * vx[B] + vy[B] * vy[B] + vz[B] * vz[B];
+    float s2 = dot3(vx[B], vy[B], vz[B], vx[B], vy[B], vz[B]);
     float pk; memcpy(&pk, &aux[ORC_AUX_PEAK2], 4);
     if (s2 > pk) memcpy(&aux[ORC_AUX_PEAK2], &s2, 4);
   }
 
   /* 4.7 write back and integrate (semi-implicit Euler; split-impulse push first) */
   for (int b = 0; b < N; b++) {
+    if (b == B && asleep) continue; /* integrateTransforms skips a sleeping body */
     vel[b].x = vx[b]; vel[b].y = vy[b]; vel[b].z = vz[b];
     if (deep) {
-      pos[b].x = pos[b].x + qx[b] * h; pos[b].y = pos[b].y + qy[b] * h; pos[b].z = pos[b].z + qz[b] * h;
+      pos[b].x = mad(qx[b], h, pos[b].x); pos[b].y = mad(qy[b], h, pos[b].y); pos[b].z = mad(qz[b], h, pos[b].z);
     }
-    pos[b].x = pos[b].x + vx[b] * h; pos[b].y = pos[b].y + vy[b] * h; pos[b].z = pos[b].z + vz[b] * h;
+    pos[b].x = mad(vx[b], h, pos[b].x); pos[b].y = mad(vy[b], h, pos[b].y); pos[b].z = mad(vz[b], h, pos[b].z);
     if (b != B) {
       float wz = vel[b].w + ew[b];
       vel[b].w = wz;
-      float yaw = pos[b].w + wz * h;
+      float yaw = mad(wz, h, pos[b].w);
       if (yaw >= TWO_PI) yaw = yaw - TWO_PI;
       else if (yaw <= -TWO_PI) yaw = yaw + TWO_PI;
       pos[b].w = yaw;
     }
   }
-  pos[B].w = wx; vel[B].w = wy;
+  if (!asleep) { pos[B].w = wx; vel[B].w = wy; }
+
+  /* 4.8 ball activation (Bullet btDiscreteDynamicsWorld::updateActivationState: btRigidBody::updateDeactivation
+   * then wantsSleeping).  Angular velocity is the spin state, identically zero in reference mode. */
+  if (asleep) {
+    vel[B].x = 0.0f; vel[B].y = 0.0f; vel[B].z = 0.0f; /* an ISLAND_SLEEPING body gets its velocities zeroed */
+    if (spin_mode) { pos[B].w = 0.0f; vel[B].w = 0.0f; }
+  } else {
+    float v2 = dot3(vel[B].x, vel[B].y, vel[B].z, vel[B].x, vel[B].y, vel[B].z);
+    float w2 = spin_mode ? dot2(pos[B].w, vel[B].w, pos[B].w, vel[B].w) : 0.0f;
+    if (v2 < SLEEP_LIN2 && w2 < SLEEP_ANG2) { if (cnt < CNT_MAX) cnt++; }
+    else { cnt = 0; act = ACT_ACTIVE; }
+    int wants = act == ACT_WANTS || (int)cnt >= sleep_substeps;
+    act = wants ? ACT_WANTS : ACT_ACTIVE;
+  }
+  aux[ORC_AUX_STATUS] = (aux[ORC_AUX_STATUS] & ((1u << ACT_SHIFT) - 1u)) | (act << ACT_SHIFT) | (cnt << CNT_SHIFT);
 }
 
 /* ---- step = substeps + events (STEP_SPEC 5) -------------------------------- */
@@ -660,10 +742,13 @@ void orc_step(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *p
               uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h) {
   field_derived d;
   derive_field(f, &d);
+  const int sleep_substeps = orc_sleep_substeps(h);
   for (int s = 0; s < n_steps; s++) {
     aux[ORC_AUX_TOUCH] = 0;
     aux[ORC_AUX_STATUS] &= ~(1u << 15);
-    for (int k = 0; k < substeps; k++) substep(&d, p, n_robots, pos, vel, aux, cmd, h);
+    /* Bullet stepSimulation: applyGravity() once, for the bodies that are active now (STEP_SPEC 3) */
+    const int ball_gravity = ((aux[ORC_AUX_STATUS] >> ACT_SHIFT) & 3u) != ACT_ASLEEP;
+    for (int k = 0; k < substeps; k++) substep(&d, p, n_robots, pos, vel, aux, cmd, h, ball_gravity, sleep_substeps);
     step_events(&d, n_robots, pos, aux);
   }
 }
@@ -682,7 +767,8 @@ int orc_referee(const orc_field *f, int R, orc_vec4 *pos, orc_vec4 *vel, uint32_
   }
   pos[B].x = x; pos[B].y = y; pos[B].z = BALL_R; pos[B].w = 0.0f;
   vel[B].x = 0.0f; vel[B].y = 0.0f; vel[B].z = 0.0f; vel[B].w = 0.0f;
-  aux[ORC_AUX_STATUS] = st & ~(7u << 8); /* not in a goal, not out: the next crossing is a new edge */
+  /* not in a goal, not out: the next crossing is a new edge; the placed ball is awake (activation bits 18..31 = 0) */
+  aux[ORC_AUX_STATUS] = st & ~(7u << 8) & ((1u << ACT_SHIFT) - 1u);
   aux[ORC_AUX_RESTARTS] += 1u;
   return 1;
 }
@@ -742,12 +828,22 @@ void orc_gen_commands(int R, uint64_t seed, uint64_t world_id, uint64_t period, 
   }
 }
 
+/* the orientation the reference's robot_get_pos reports (src/sslsim.cpp:437-443): sign(axis.z) * getAngle() of the
+ * quaternion btMatrix3x3::getRotation extracts -- yaw wrapped to (-pi, pi], except that (-pi, -2pi/3) comes back
+ * as 2pi - |yaw| (negative-w quaternion of the largest-diagonal branch), and yaw 0 reads -0.0 (identity axis (1,0,0)) */
+float orc_readout_yaw(float yaw) {
+  float k = rintf(yaw * 0.15915494f);
+  float t = yaw - k * TWO_PI;
+  if (t < -2.0943952f) t = t + TWO_PI;
+  return t == 0.0f ? -0.0f : t;
+}
+
 int orc_gather(int R, const orc_vec4 *pos, const int *ids, float *out) {
   int n = 0;
   const orc_vec4 *b = &pos[R];
   out[n++] = 1.0f; out[n++] = b->x; out[n++] = b->y; out[n++] = b->z; out[n++] = b->x; out[n++] = b->y;
   for (int r = 0; r < R; r++) {
-    float yaw = pos[r].w == 0.0f ? -0.0f : pos[r].w; /* reference src/sslsim.cpp:441-442 quirk */
+    float yaw = orc_readout_yaw(pos[r].w);
     out[n++] = 1.0f; out[n++] = (float)ids[r];
     out[n++] = pos[r].x; out[n++] = pos[r].y; out[n++] = yaw; out[n++] = pos[r].x; out[n++] = pos[r].y;
   }

@@ -49,7 +49,8 @@ typedef struct {
   float wheel_kp, wheel_fmax, robot_yaw_inertia;
   float dribble_kd, dribble_cd, dribble_amax, dribble_reach;
   float mu_roll;
-  float reserved[3];
+  float restitution_threshold; /* Bullet m_restitutionVelocityThreshold: 0 = Bullet 2.82 (none); 0.2 = Bullet >= 2.87 */
+  float reserved[2];
 } orc_params;
 
 /* per robot command, 32 bytes; schema: reference protos/grSim_Commands.proto:1-14 */
@@ -70,7 +71,9 @@ typedef struct {
 enum {
   ORC_AUX_STATUS = 0, /* [7:0] last touching robot (0xFF none); bit8/9/10 prev in +x goal / -x goal / out;
                          bits12..15 events of the last step: goal_blue, goal_yellow, out, kicked;
-                         bit16 row overflow (sticky); bit17 non-finite state (sticky) */
+                         bit16 row overflow (sticky); bit17 non-finite state (sticky);
+                         bits18..19 ball activation state (0 active, 1 wants deactivation, 2 asleep);
+                         bits20..31 consecutive substeps with the ball below the sleeping thresholds */
   ORC_AUX_PEAK2 = 1,  /* f32 bits: peak |v_ball|^2 since last kick */
   ORC_AUX_TOUCH = 2,  /* robots that touched the ball during the last step (bit i = robot i) */
   ORC_AUX_RESTARTS = 3, /* restarts placed by orc_referee */
@@ -105,12 +108,17 @@ void orc_gen_commands(int n_robots, uint64_t seed, uint64_t world_id,
  * 6 floats per ball {conf,x,y,z,px,py} then 7 per robot {conf,id,x,y,yaw,px,py}
  * in world robot order.  ids: robot ids. Returns number of floats. */
 int orc_gather(int n_robots, const orc_vec4 *pos, const int *ids, float *out);
+float orc_readout_yaw(float yaw); /* Bullet's matrix -> quaternion -> sign(axis.z) * angle readout, range (-2pi/3, 4pi/3) */
 
 /* referee restart placement (STEP_SPEC 7, builder-defined): if the last step raised a goal event the ball goes to
  * the centre spot, if it raised ball-out the ball goes back 0.1 m inside the line it crossed; placed at rest
  * on the ground (z = ball radius, zero velocity and spin), in-goal/out edge state cleared, aux[3]++.
  * Returns 1 if the ball was re-placed. */
 int orc_referee(const orc_field *f, int n_robots, orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux);
+
+/* number of substeps of length h after which Bullet's m_deactivationTime (binary32 accumulation) first exceeds
+ * gDeactivationTime = 2 s; 4096 if that is beyond the 12-bit counter */
+int orc_sleep_substeps(float h);
 
 /* splitmix64-keyed uniform in [0,1) with 24 bits */
 float orc_u01(uint64_t seed, uint64_t a, uint64_t b, uint64_t c);

@@ -52,7 +52,8 @@ class SimParams(C.Structure):
                 ("kick_reach", C.c_float), ("kick_halfwidth", C.c_float), ("kick_max_height", C.c_float),
                 ("wheel_kp", C.c_float), ("wheel_fmax", C.c_float), ("robot_yaw_inertia", C.c_float),
                 ("dribble_kd", C.c_float), ("dribble_cd", C.c_float), ("dribble_amax", C.c_float),
-                ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("reserved", C.c_float * 3)]
+                ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("restitution_threshold", C.c_float),
+                ("reserved", C.c_float * 2)]
 
 
 class Vec2(C.Structure):

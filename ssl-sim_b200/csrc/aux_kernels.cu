@@ -107,7 +107,7 @@ __global__ void replace_robots(float4 *pos, int W, int R, const RobotReplacement
   pos[(size_t)rec.world * (R + 1) + rec.robot] = make_float4(rec.x, rec.y, DROP_Z, rec.dir);
 }
 
-__global__ void replace_balls(float4 *pos, float4 *vel, int W, int R, const BallReplacement *recs, int n) {
+__global__ void replace_balls(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, const BallReplacement *recs, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const BallReplacement rec = recs[t];
@@ -117,6 +117,7 @@ __global__ void replace_balls(float4 *pos, float4 *vel, int W, int R, const Ball
   const size_t i = (size_t)rec.world * (R + 1) + R;
   pos[i] = make_float4(rec.x, rec.y, DROP_Z, 0.0f);
   vel[i] = make_float4(rec.vx, rec.vy, 0.0f, 0.0f);
+  aux[(size_t)rec.world * 8 + SSLSIM_AUX_STATUS] &= SSLSIM_STATUS_KEEP_ON_WAKE; /* reference :387 body.activate(true) */
 }
 
 /* K3: one warp per observed world; record = 6 floats ball + 7 floats per robot */
@@ -138,7 +139,7 @@ __global__ void gather_detections(const float4 *pos, int W, int R, const int *wo
       o[0] = 1.0f; o[1] = q.x; o[2] = q.y; o[3] = q.z; o[4] = q.x; o[5] = q.y;
     } else {
       float *r = o + 6 + 7 * b;
-      const float yaw = q.w == 0.0f ? -0.0f : q.w; /* reference src/sslsim.cpp:440-442: sign(axis.z) * angle at yaw 0 */
+      const float yaw = sslsim_readout_yaw(q.w); /* reference src/sslsim.cpp:440-442 */
       r[0] = 1.0f; r[1] = (float)robot_ids[b]; r[2] = q.x; r[3] = q.y; r[4] = yaw; r[5] = q.x; r[6] = q.y;
     }
   }
@@ -163,7 +164,7 @@ __global__ void referee_restart(float4 *pos, float4 *vel, uint32_t *aux, int W, 
   }
   pos[i] = make_float4(x, y, BALL_R, 0.0f);
   vel[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  a[SSLSIM_AUX_STATUS] = st & ~(7u << 8);
+  a[SSLSIM_AUX_STATUS] = st & ~(7u << 8) & SSLSIM_STATUS_KEEP_ON_WAKE; /* edge state cleared; the placed ball is awake */
   a[SSLSIM_AUX_RESTARTS] += 1u;
 }
 
@@ -245,10 +246,10 @@ cudaError_t sslsim_launch_replace_robots(float4 *pos, int W, int R, const RobotR
   return cudaGetLastError();
 }
 
-cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, int W, int R, const BallReplacement *recs,
+cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, const BallReplacement *recs,
                                         int n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  replace_balls<<<(n + 127) / 128, 128, 0, s>>>(pos, vel, W, R, recs, n);
+  replace_balls<<<(n + 127) / 128, 128, 0, s>>>(pos, vel, aux, W, R, recs, n);
   return cudaGetLastError();
 }
 

@@ -37,7 +37,7 @@ bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what) {
     if (!sslsim_check(b, (call), #call)) return SSLSIM_E_CUDA;     \
   } while (0)
 /* work queued on chunk streams is ordered before anything that follows on the batch stream */
-static int join_chunks(WorldBatch *b) {
+int sslsim_join_chunks(WorldBatch *b) {
   for (WorldBatch::Chunk &c : b->chunks) {
     if (!c.dirty) continue;
     if (!sslsim_check(b, cudaEventRecord(c.done, c.stream), "chunk record") ||
@@ -52,7 +52,7 @@ static int join_chunks(WorldBatch *b) {
   cudaSetDevice((b)->device)
 #define ENTER(b)                                  \
   ENTER_NOJOIN(b);                                \
-  if (!(b)->chunks.empty() && join_chunks(b)) return SSLSIM_E_CUDA
+  if (!(b)->chunks.empty() && sslsim_join_chunks(b)) return SSLSIM_E_CUDA
 
 static void free_chunks(WorldBatch *b) {
   for (WorldBatch::Chunk &c : b->chunks) {
@@ -417,7 +417,7 @@ int world_batch_replace_balls(struct WorldBatch *b, const struct BallReplacement
   int rc = ensure_rep(b, (size_t)n * sizeof(BallReplacement));
   if (rc) return rc;
   CK(cudaMemcpyAsync(b->d_rep, recs, (size_t)n * sizeof(BallReplacement), cudaMemcpyHostToDevice, b->stream));
-  CK(sslsim_launch_replace_balls(b->d_pos, b->d_vel, b->W, b->R, (const BallReplacement *)b->d_rep, n, b->stream));
+  CK(sslsim_launch_replace_balls(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, (const BallReplacement *)b->d_rep, n, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;
@@ -502,6 +502,7 @@ struct WorldSnapshot {
 struct WorldSnapshot *world_batch_snapshot(struct WorldBatch *b) {
   if (!b || b->last_error == SSLSIM_E_CUDA) return nullptr;
   cudaSetDevice(b->device);
+  if (!b->chunks.empty() && sslsim_join_chunks(b)) return nullptr; /* after all queued chunk work */
   WorldSnapshot *s = new (std::nothrow) WorldSnapshot();
   if (!s) return nullptr;
   s->device = b->device; s->W = b->W; s->R = b->R; s->frame = b->frame; s->timestamp = b->timestamp;

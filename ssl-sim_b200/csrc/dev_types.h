@@ -31,11 +31,30 @@ struct StepArgs {
   /* launch invariants derived from h on the host (IEEE fp32, the same values the kernel would compute): they
    * are read as constant-bank operands instead of occupying registers for the whole launch */
   float inv_h, gh, h_over_m, h_over_inertia, ez;
+  int sleep_substeps;    /* slow substeps after which the ball wants to sleep (Bullet: > 2 s) */
   DevField f;            /* by value: constant bank */
   const DevField *f_dev; /* the same in global memory, for the out-of-line general path */
   SslSimParams p;
   unsigned *prof; /* SSLSIM_PROFILE builds: [W][8] per-world counters, else unused */
 };
+
+/* status-word bits that survive waking the ball (everything below the activation state / slow-substep count) */
+#define SSLSIM_STATUS_KEEP_ON_WAKE 0x3ffffu
+
+/* The orientation robot_get_pos reports (reference src/sslsim.cpp:437-443): sign(axis.z) * btQuaternion::getAngle()
+ * of the quaternion btMatrix3x3::getRotation extracts.  For a rotation about z by t in (-pi, pi] that is t itself
+ * while cos t > -1/2 (trace branch) and for t >= 2pi/3; for t in (-pi, -2pi/3) the largest-diagonal branch yields a
+ * quaternion with negative w and the call returns 2pi - |t|.  Bullet's identity rotation has axis (1,0,0), so yaw 0
+ * reads -0.0.  Range (-2pi/3, 4pi/3).  Same arithmetic on host and device (no contraction). */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline float sslsim_readout_yaw(float yaw) {
+  const float k = rintf(yaw * 0.15915494f);
+  float t = yaw - k * 6.2831855f;
+  if (t < -2.0943952f) t = t + 6.2831855f;
+  return t == 0.0f ? -0.0f : t;
+}
 
 void sslsim_derive_field(const FieldGeometry *g, DevField *d);
 void sslsim_step_invariants(StepArgs *a, const SslSimParams &p); /* fills inv_h ... ez from a->h (step_kernel.cu) */
@@ -48,7 +67,7 @@ cudaError_t sslsim_launch_gen_commands(RobotCommand *cmd, int n_worlds, int n_ro
                                        uint64_t world0, uint64_t period, int kind, cudaStream_t s);
 cudaError_t sslsim_launch_replace_robots(float4 *pos, int n_worlds, int n_robots, const RobotReplacement *recs,
                                          int n, cudaStream_t s);
-cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, int n_worlds, int n_robots,
+cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots,
                                         const BallReplacement *recs, int n, cudaStream_t s);
 cudaError_t sslsim_launch_gather(const float4 *pos, int n_worlds, int n_robots, const int *world_ids, int n,
                                  const int *robot_ids, float *out, cudaStream_t s);

@@ -37,26 +37,32 @@ float u01(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
 
 WorldBatch *B(const World *w) { return w->batch; }
 
-/* device -> host mirror of this world's slice */
+/* device -> host mirror of this world's slice.  Ordered after everything queued on the batch, chunk streams
+ * included.  On failure (sticky CUDA error) the mirror is zeroed, so the reference-style getters -- which have no
+ * way to report an error -- return zeros instead of stale state; world_batch_last_error() tells why. */
 bool pull(World *w) {
   if (w->mirror_valid) return true;
   WorldBatch *b = B(w);
-  if (b->last_error == SSLSIM_E_CUDA) return false;
-  cudaSetDevice(b->device);
   const int N = b->R + 1;
+  if (b->last_error == SSLSIM_E_CUDA || sslsim_join_chunks(b) != SSLSIM_OK) {
+    memset(w->pos, 0, sizeof w->pos); memset(w->vel, 0, sizeof w->vel); memset(w->aux, 0, sizeof w->aux);
+    return false;
+  }
+  cudaSetDevice(b->device);
   const size_t off = (size_t)w->index * N;
   bool ok = sslsim_check(b, cudaMemcpyAsync(w->pos, b->d_pos + off, N * sizeof(float4), cudaMemcpyDeviceToHost, b->stream), "pull pos") &&
             sslsim_check(b, cudaMemcpyAsync(w->vel, b->d_vel + off, N * sizeof(float4), cudaMemcpyDeviceToHost, b->stream), "pull vel") &&
             sslsim_check(b, cudaMemcpyAsync(w->aux, b->d_aux + (size_t)w->index * 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream), "pull aux") &&
             sslsim_check(b, cudaStreamSynchronize(b->stream), "pull sync");
   w->mirror_valid = ok;
+  if (!ok) { memset(w->pos, 0, sizeof w->pos); memset(w->vel, 0, sizeof w->vel); memset(w->aux, 0, sizeof w->aux); }
   return ok;
 }
 
 /* host mirror -> device */
 bool push(World *w) {
   WorldBatch *b = B(w);
-  if (b->last_error == SSLSIM_E_CUDA) return false;
+  if (b->last_error == SSLSIM_E_CUDA || sslsim_join_chunks(b) != SSLSIM_OK) return false;
   cudaSetDevice(b->device);
   const int N = b->R + 1;
   const size_t off = (size_t)w->index * N;
@@ -154,12 +160,17 @@ void world_step_delta(struct World *world, Float time_step, int max_substeps, Fl
     h = time_step;
     n = fabsf(time_step) < 1.1920929e-07f ? 0 : 1;
   }
-  if (world->owns_batch) {
-    sslsim_batch_step(b, 1, n, h, time_step);
-  } else {
-    fprintf(stderr, "sslsim_b200: world_step on a batch member steps the whole batch; use world_batch_step\n");
-    sslsim_batch_step(b, 1, n, h, time_step);
+  if (!world->owns_batch) {
+    /* a view of a batch member shares the batch's clock and launch: stepping one member alone would tear the
+     * lockstep, stepping all of them behind the caller's back is worse.  Refused: no state changes, the batch
+     * reports SSLSIM_E_ARG (not sticky) through world_batch_last_error(). */
+    world->local_time = 0.0f;
+    b->last_error = SSLSIM_E_ARG;
+    snprintf(b->errstr, sizeof b->errstr, "world_step on a batch member view is not supported; use world_batch_step");
+    fprintf(stderr, "sslsim_b200: %s\n", b->errstr);
+    return;
   }
+  sslsim_batch_step(b, 1, n, h, time_step);
   world->mirror_valid = false;
 }
 
@@ -233,6 +244,7 @@ void ball_set_vec(struct Ball *ball, const struct Vec2 vec) { /* reference :384-
   if (!pull(w)) return;
   float *p = w->pos[BI(ball)];
   p[0] = vec.x; p[1] = vec.y; p[2] = DROP_Z;
+  w->aux[SSLSIM_AUX_STATUS] &= SSLSIM_STATUS_KEEP_ON_WAKE; /* :387 body.activate(true) */
   push(w);
 }
 
@@ -248,6 +260,7 @@ void ball_set_pos(struct Ball *ball, const struct Pos3 pos) {
   if (!pull(w)) return;
   float *p = w->pos[BI(ball)];
   p[0] = pos.x; p[1] = pos.y; p[2] = pos.z;
+  w->aux[SSLSIM_AUX_STATUS] &= SSLSIM_STATUS_KEEP_ON_WAKE;
   push(w);
 }
 
@@ -263,6 +276,7 @@ void ball_set_vel(struct Ball *ball, const struct Pos3 vel) {
   if (!pull(w)) return;
   float *p = w->pos[BI(ball)], *v = w->vel[BI(ball)];
   v[0] = vel.x; v[1] = vel.y; v[2] = vel.z; p[3] = vel.wx; v[3] = vel.wy;
+  w->aux[SSLSIM_AUX_STATUS] &= SSLSIM_STATUS_KEEP_ON_WAKE;
   push(w);
 }
 
@@ -305,8 +319,7 @@ struct Pos2 robot_get_pos(const struct Robot *robot) { /* reference src/sslsim.c
   World *w = robot->world;
   pull(w);
   const float *p = w->pos[robot->index];
-  /* sign(axis.z) * angle: Bullet's axis for the identity rotation is (1,0,0), so yaw 0 reads -0.0 */
-  return Pos2{p[0], p[1], p[3] == 0.0f ? -0.0f : p[3]};
+  return Pos2{p[0], p[1], sslsim_readout_yaw(p[3])};
 }
 
 void robot_set_pos(struct Robot *robot, const struct Pos2 pos) { /* reference :445-450: re-drop, velocity kept */

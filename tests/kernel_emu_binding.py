@@ -29,7 +29,7 @@ def lib():
         L = C.CDLL(os.path.join(EMU_DIR, "libstep_kernel_emu.so"))
         vp = C.c_void_p
         L.emu_step_worlds.argtypes = [C.POINTER(ob.Field), C.POINTER(ob.Params), C.c_int, C.c_int, vp, vp, vp, vp,
-                                      C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_longlong, C.c_int]
+                                      C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_longlong, C.c_int, vp]
         L.emu_step_worlds.restype = C.c_int
         _LIB = L
     return _LIB
@@ -39,10 +39,10 @@ class EmuWorlds(ob.Worlds):
     """Same initial state / command generator as the oracle's Worlds (those are tested against the CUDA init and
     gen_commands kernels on the GPU); only step() runs the emulated kernel."""
 
-    def step(self, n_steps=1, substeps=2, h=ob.H, lanes=0, threads=8, cmd_seq=None, steps_per_period=0):
+    def step(self, n_steps=1, substeps=2, h=ob.H, lanes=0, threads=8, cmd_seq=None, steps_per_period=0, prof=None):
         cmd = self.cmd if cmd_seq is None else cmd_seq
         stride = self.W * self.R if cmd_seq is not None else 0
         rc = lib().emu_step_worlds(C.byref(self.field), C.byref(self.params), self.R, self.W, ob._ptr(self.pos),
                                    ob._ptr(self.vel), ob._ptr(self.aux), ob._ptr(cmd), n_steps, substeps,
-                                   C.c_float(float(h)), lanes, steps_per_period, stride, threads)
+                                   C.c_float(float(h)), lanes, steps_per_period, stride, threads, ob._ptr(prof))
         assert rc == 0

@@ -34,7 +34,8 @@ class Params(C.Structure):
                 ("kick_reach", C.c_float), ("kick_halfwidth", C.c_float), ("kick_max_height", C.c_float),
                 ("wheel_kp", C.c_float), ("wheel_fmax", C.c_float), ("robot_yaw_inertia", C.c_float),
                 ("dribble_kd", C.c_float), ("dribble_cd", C.c_float), ("dribble_amax", C.c_float),
-                ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("reserved", C.c_float * 3)]
+                ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("restitution_threshold", C.c_float),
+                ("reserved", C.c_float * 2)]
 
 
 CMD_DTYPE = np.dtype([("wheel", np.float32, 4), ("kickspeedx", np.float32), ("kickspeedz", np.float32),
@@ -63,6 +64,10 @@ def lib():
         L.orc_gather.restype = C.c_int
         L.orc_referee.argtypes = [C.POINTER(Field), C.c_int, fp, fp, fp]
         L.orc_referee.restype = C.c_int
+        L.orc_readout_yaw.argtypes = [C.c_float]
+        L.orc_readout_yaw.restype = C.c_float
+        L.orc_sleep_substeps.argtypes = [C.c_float]
+        L.orc_sleep_substeps.restype = C.c_int
         L.orc_u01.argtypes = [C.c_uint64] * 4
         L.orc_u01.restype = C.c_float
         L.orc_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -70,6 +75,11 @@ def lib():
                                     C.c_int, C.c_int, C.c_float, C.c_int]
         _LIB = L
     return _LIB
+
+
+def readout_yaw(yaw):
+    """the orientation robot_get_pos / the detection gather report for a state yaw (Bullet's quaternion readout)"""
+    return np.float32(lib().orc_readout_yaw(C.c_float(float(yaw))))
 
 
 def field(vals=FIELD_2015):

@@ -310,7 +310,7 @@ def test_legacy_single_world_api(sim, orc):
     for i in range(12):
         x, y, yaw = w.robot_pos(i)
         assert (np.float32(x), np.float32(y)) == (o.pos[0, i, 0], o.pos[0, i, 1])
-        assert np.float32(yaw) == o.pos[0, i, 3]
+        assert np.float32(yaw) == orc.readout_yaw(o.pos[0, i, 3])
         assert L.get_id(w.robot(i)) == i // 2 and L.get_team(w.robot(i)) == i % 2
     assert tuple(np.float32(v) for v in w.ball_vec()) == tuple(o.pos[0, 12, :3])
     # replacement through the legacy setters: re-dropped from 0.5 m, velocity untouched
@@ -318,6 +318,7 @@ def test_legacy_single_world_api(sim, orc):
     L.ball_set_vec(w.ball(), sim.Vec2(-1.0, 0.5))
     o.pos[0, 3] = (1.0, 2.0, 0.5, 0.7)
     o.pos[0, 12, :3] = (-1.0, 0.5, 0.5)
+    o.aux[0, 0] &= 0x3FFFF      # ball_set_vec wakes the ball (reference src/sslsim.cpp:387 activate(true))
     c = w.clone()
     for _ in range(60):
         w.step(); c.step()
@@ -376,7 +377,7 @@ def test_c_client_runs_like_reference_cli(sim, orc, tmp_path):
     for i in range(12):
         f = out[2 + i].split()
         assert (int(f[1]), int(f[2])) == (i // 2, i % 2)
-        assert [np.float32(v) for v in f[3:]] == list(o.pos[0, i, [0, 1, 3]])
+        assert [np.float32(v) for v in f[3:]] == [o.pos[0, i, 0], o.pos[0, i, 1], orc.readout_yaw(o.pos[0, i, 3])]
     sizes = [int(v) for v in out[14].split()[1:]]
     assert 440 < sizes[0] < 500 and 20 < sizes[1] < 60      # detection ~475 B, geometry packet
 
@@ -397,7 +398,7 @@ def test_serialize_world_and_batch(sim, orc):
         assert (np.float32(d.balls[0].x), np.float32(d.balls[0].y), np.float32(d.balls[0].z)) == tuple(o.pos[w, R, :3])
         assert len(d.robots_blue) == 6 and len(d.robots_yellow) == 6
         for k, m in enumerate(d.robots_yellow):
-            assert m.robot_id == k and (np.float32(m.x), np.float32(m.orientation)) == (o.pos[w, 2 * k + 1, 0], o.pos[w, 2 * k + 1, 3])
+            assert m.robot_id == k and (np.float32(m.x), np.float32(m.orientation)) == (o.pos[w, 2 * k + 1, 0], orc.readout_yaw(o.pos[w, 2 * k + 1, 3]))
     v = b.get_world(3)
     d = pb["SSL_WrapperPacket"].FromString(v.serialize()).detection
     assert d.frame_number == 75 and np.float32(d.robots_blue[2].y) == o.pos[3, 4, 1] and d.t_sent > 1.5e9
@@ -741,7 +742,8 @@ def test_legacy_accessors_on_batch_members(sim, orc):
     # getters
     for i in (0, 7, 11):
         p = L.robot_get_pos(w5.robot(i)); v = L.robot_get_vel(w5.robot(i))
-        assert (np.float32(p.x), np.float32(p.y), np.float32(p.w)) == tuple(o.pos[5, i, [0, 1, 3]])
+        assert (np.float32(p.x), np.float32(p.y)) == tuple(o.pos[5, i, [0, 1]])
+        assert np.float32(p.w) == orc.readout_yaw(o.pos[5, i, 3])
         assert (np.float32(v.x), np.float32(v.y), np.float32(v.w)) == tuple(o.vel[5, i, [0, 1, 3]])
         assert np.float32(L.robot_get_speed2(w5.robot(i))) == np.float32(np.float32(np.float32(o.vel[5, i, 0] * o.vel[5, i, 0]) + np.float32(o.vel[5, i, 1] * o.vel[5, i, 1])) + np.float32(o.vel[5, i, 2] * o.vel[5, i, 2]))
     bp, bv = L.ball_get_pos(w5.ball()), L.ball_get_vel(w5.ball())
@@ -761,6 +763,10 @@ def test_legacy_accessors_on_batch_members(sim, orc):
     L.ball_set_vel(w5.ball(), sim.Pos3(2.0, 0.5, 1.0, 0, 0, 0))
     L.robot_set_vel(w5.robot(2), sim.Pos2(-1.0, 0.25, 3.0))
     o.pos[5, R, :3] = (1.0, -1.0, 0.3); o.vel[5, R, :3] = (2.0, 0.5, 1.0)
+    o.aux[5, 0] &= 0x3FFFF      # the ball setters wake the ball
+    # world_step on a member view is refused (it would tear the batch's lockstep): no state change, E_ARG reported
+    L.world_step(w5._h)
+    assert L.world_batch_last_error(b._h) == -1 and w5.frame_number == 120
     o.vel[5, 2, [0, 1, 3]] = (-1.0, 0.25, 3.0)
     # two robots side by side: touching by geometry
     w2 = b.get_world(2)

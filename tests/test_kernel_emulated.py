@@ -85,3 +85,33 @@ def test_emulated_kernel_kick_and_goal_area():
         o.step(1); e.step(1)
     _same(o, e)
     assert int((o.aux[:, 5] >> 16).sum()) > 0   # kicks happened
+
+
+@pytest.mark.parametrize("flags", [0, ob.F_BALL_SPIN])
+def test_emulated_kernel_ball_sleep_and_wake(flags):
+    """balls fall asleep 2 s after they stopped (STEP_SPEC 4.0 / 4.8) and roaming robots wake them again"""
+    kw = dict(params=ob.default_params(flags=flags))
+    o, e = _pair(32, 12, **kw)
+    states = set()
+    woken = 0
+    prev = None
+    for p in range(30):
+        o.gen_commands(p, 0); e.gen_commands(p, 0)
+        o.step(30); e.step(30)
+        _same(o, e, "period %d" % p)
+        act = (o.aux[:, 0] >> 18) & 3
+        states |= set(int(a) for a in act)
+        if prev is not None:
+            woken += int(((prev == 2) & (act != 2)).sum())
+        prev = act
+    assert 2 in states            # some ball slept
+    assert woken > 0              # and some sleeping ball was woken by a robot
+
+
+def test_emulated_kernel_restitution_threshold_parameter():
+    kw = dict(params=ob.default_params(restitution_threshold=0.2))
+    o, e = _pair(8, 12, **kw)
+    for p in range(4):
+        o.gen_commands(p, 1); e.gen_commands(p, 1)
+        o.step(40); e.step(40)
+    _same(o, e)

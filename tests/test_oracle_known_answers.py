@@ -11,6 +11,13 @@ import pytest
 
 G = np.float32(9.80665)
 H = np.float32(1.0 / 60 / 2)
+_fmaf = C.CDLL("libm.so.6").fmaf            # an independent fused multiply-add (STEP_SPEC section 0)
+_fmaf.restype = C.c_float
+_fmaf.argtypes = [C.c_float] * 3
+
+
+def fma32(a, b, c):
+    return np.float32(_fmaf(float(a), float(b), float(c)))
 
 
 def _one_world(orc, R=0, **kw):
@@ -25,7 +32,7 @@ def test_free_fall_semi_implicit_euler(orc):
     for n in range(30):
         w.step(1, substeps=1)
         v = np.float32(v + (np.float32(0.0) - np.float32(G * H)))
-        z = np.float32(z + np.float32(v * H))
+        z = fma32(v, H, z)       # position integration is one fused multiply-add (STEP_SPEC 0, 4.7)
         assert w.vel[0, 0, 2] == v and w.pos[0, 0, 2] == z, n
     # closed form: z_n = 0.5 - g h^2 n(n+1)/2
     assert abs(float(z) - (0.5 - 9.80665 * float(H) ** 2 * 30 * 31 / 2)) < 1e-5
@@ -198,3 +205,77 @@ def test_energy_does_not_grow_without_commands(orc):
         e1 = energy()
         assert (e1 <= e0 + 1e-3).all()
         e0 = e1
+
+
+def _act(w, k=0):
+    st = int(w.aux[k, 0])
+    return (st >> 18) & 3, st >> 20
+
+
+def test_ball_goes_to_sleep_after_two_seconds(orc):
+    """The reference ball is not DISABLE_DEACTIVATION (src/sslsim.cpp:51-61; robots are, :113): Bullet puts it to
+    sleep once it has stayed below 0.8 m/s for more than 2 s (binary32 accumulation of h = 1/120: 241 substeps) and
+    no robot shares its island.  Asleep = velocity exactly zero, no gravity, no contact row, no integration."""
+    assert orc.lib().orc_sleep_substeps(H) == 241
+    w = orc.Worlds(1, 1)
+    w.pos[0, 0] = (3.0, 2.0, 0.025, 0.0)        # robot far away, at rest
+    w.pos[0, 1] = (0.0, 0.0, 0.0215, 0.0)       # ball at rest on the ground
+    w.step(120)                                  # 240 slow substeps: not yet
+    assert _act(w) == (0, 240)
+    w.step(1, substeps=1)                        # 241st: m_deactivationTime > 2 -> wants deactivation
+    assert _act(w) == (1, 241)
+    c0 = int(w.aux[0, 7])
+    w.step(1, substeps=1)                        # next island build: alone -> asleep, velocities zeroed
+    assert _act(w)[0] == 2
+    assert (w.vel[0, 1, :3] == 0).all()
+    assert int(w.aux[0, 7]) - c0 == 1            # only the robot's ground row was solved
+    z = w.pos[0, 1, 2].copy()
+    w.step(60)
+    assert _act(w)[0] == 2 and w.pos[0, 1, 2] == z and (w.vel[0, 1, :3] == 0).all()
+
+
+def test_moving_ball_does_not_sleep_and_robot_wakes_it(orc):
+    w = orc.Worlds(1, 1)
+    w.pos[0, 0] = (3.0, 2.0, 0.025, 0.0)
+    w.pos[0, 1] = (0.0, 0.0, 0.0215, 0.0)
+    w.vel[0, 1, 0] = 3.0                         # sliding: above 0.8 m/s for ~0.9 s
+    w.step(30)
+    assert _act(w) == (0, 0)
+    w.step(600)
+    assert _act(w)[0] == 2                       # stopped, then slept
+    # a robot whose shapes come within the broadphase margins of the ball wakes it: asleep -> wants, time 0
+    bx = float(w.pos[0, 1, 0])
+    w.pos[0, 0, :2] = (bx + 0.15, 0.0)
+    w.step(1, substeps=1)
+    assert _act(w) == (1, 1) and float(w.vel[0, 1, 2]) == 0.0   # awake, but gravity was not applied this step
+    w.step(1)
+    assert _act(w)[0] == 1 and abs(float(w.vel[0, 1, 2])) < 1e-6
+    w.pos[0, 0, :2] = (bx + 1.0, 0.0)            # the robot leaves: the drowsy ball sleeps at once
+    w.step(1, substeps=1)
+    assert _act(w)[0] == 2
+
+
+def test_restitution_threshold_is_a_bullet_version_switch(orc):
+    """Bullet 2.82 (the spec's column): restitution e*(-vn) for any approach speed.  0.2 (Bullet >= 2.87's
+    m_restitutionVelocityThreshold) is available as a parameter."""
+    out = []
+    for thr in (0.0, 0.2):
+        w = orc.Worlds(1, 0, params=orc.default_params(restitution_threshold=thr))
+        w.pos[0, 0, 2] = 0.0215 + 0.0005
+        w.vel[0, 0, 2] = -0.1                    # slow approach: below 0.2 m/s
+        w.step(1, substeps=1)
+        out.append(float(w.vel[0, 0, 2]))
+    assert out[0] == pytest.approx(0.05, rel=1e-3)      # bounces with e = 0.5
+    assert out[1] <= 0.0                                # no restitution below the threshold
+
+
+def test_readout_yaw_follows_bullets_quaternion_readout(orc):
+    """robot_get_pos reports sign(axis.z) * getAngle() of the quaternion btMatrix3x3::getRotation extracts
+    (reference src/sslsim.cpp:437-443): yaw wrapped to (-pi, pi], except that (-pi, -2pi/3) comes back as
+    2pi - |yaw|; the identity reads -0.0."""
+    two_pi = 2 * np.pi
+    for yaw, want in [(0.5, 0.5), (5.0, 5.0 - two_pi), (4.0, 4.0), (3.5, 3.5), (-3.0, two_pi - 3.0), (-2.0, -2.0),
+                      (-6.0, two_pi - 6.0), (2.5, 2.5), (-2.2, two_pi - 2.2)]:
+        assert float(orc.readout_yaw(yaw)) == pytest.approx(want, abs=1e-6), yaw
+    z = orc.readout_yaw(0.0)
+    assert z == 0.0 and np.signbit(z)

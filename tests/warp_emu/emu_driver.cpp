@@ -8,7 +8,7 @@
 extern "C" int emu_step_worlds(const FieldGeometry *field, const SslSimParams *params, int n_robots, int n_worlds,
                                float *pos, float *vel, uint32_t *aux, const RobotCommand *cmd, int n_steps,
                                int substeps, float h, int lanes, int steps_per_period, long long cmd_period_stride,
-                               int os_threads) {
+                               int os_threads, unsigned *prof) {
   static DevField dfield; /* f_dev points here ("global memory" of the out-of-line general path) */
   StepArgs a;
   memset(&a, 0, sizeof a);
@@ -18,7 +18,7 @@ extern "C" int emu_step_worlds(const FieldGeometry *field, const SslSimParams *p
   a.steps_per_period = steps_per_period; a.cmd_period_stride = cmd_period_stride;
   a.p = *params;
   sslsim_step_invariants(&a, a.p);
-  a.f = dfield; a.f_dev = &dfield; a.prof = nullptr;
+  a.f = dfield; a.f_dev = &dfield; a.prof = prof; /* per-world counters of -DSSLSIM_PROFILE builds, else unused */
   int threads = os_threads;
   return (int)sslsim_launch_step(a, lanes, (cudaStream_t)&threads);
 }
