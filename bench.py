@@ -1,33 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- world-steps/sec of the batched SSL world-stepper (BASELINE.json metric).
+"""bench.py -- world-steps/sec of the batched SSL world-stepper (BASELINE.json metric), strong scaling.
 
-Workload (BASELINE.json configs[1]): 4,096 batched 6v6 worlds per GPU on
-FIELD_2015 with randomized wheel-velocity commands that are redrawn every 30 world-steps.
-One bench *step* = one command batch + 30 world-steps of every world.  One world-step = one `world_step` of the reference
-(reference src/sslsim.cpp:307-310: 1/60 s, two 1/120 s substeps).
+Workload = BASELINE.json configs[4]: 1,048,576 6v6 worlds on FIELD_2015 in total, sharded
+over the N GPUs in contiguous ranges (N = 1: all of them on one GPU), randomized wheel-velocity commands redrawn every
+30 world-steps, no per-step collective, one all-gather of the episode statistics at the end.
+One bench *step* = 10 command periods x 30 world-steps = 300 world-steps of every world.  One world-step = one
+`world_step` of the reference (src/sslsim.cpp:307-310: 1/60 s, two 1/120 s substeps).
 
-  value     device-resident arm: the K command batches are staged in HBM before the timed region and
-            consumed `--periods-per-launch` (default 10) at a time by one `step_worlds` launch
-            (world_batch_step_sequence: every world runs through its periods without a batch-wide
-            barrier); CUDA events bracket each launch on the batch's own stream; L2 is flushed between
-            launches (outside the event pairs).  `one_launch_per_period` is the same K steps with one
-            launch per command period -- what a closed-loop caller (and the e2e arm) does.
-  e2e       the same work through the C ABI with HOST buffers, closed loop: per step the command batch is
-            copied from pinned host memory, stepped, and the per-world event / statistics words are read
-            back to host memory; wall time of K steps.  The batch is driven as `--e2e-chunks` (default 8)
-            contiguous chunks of worlds, each on its own CUDA stream (world_batch_chunk_step /
-            world_batch_chunk_wait): the host waits for a chunk's results of step k before it submits
-            that chunk's step k+1, while the other chunks' copies and launches keep the GPU busy.
-            `e2e.whole_batch` is the same loop with one stream and a batch-wide barrier per step
-            (world_batch_set_commands + world_batch_step + world_batch_read_aux).
-  roofline  algorithmic bytes (1,232 B per 6v6 world-step) / kernel duration vs the
-            measured HBM copy bandwidth.
-  cpu_baseline  the CPU oracle (restated-Bullet port; Bullet itself is not buildable here) on the
-            host cores for a bounded sample of the same workload.
+  value     device-resident arm: the 10 command blocks of a step are generated into HBM (outside the event pair), then
+            ONE step_worlds launch runs the 300 world-steps (world_batch_step_sequence); CUDA events bracket each launch on
+            the batch's own stream; max over ranks of the summed launch times.  The working set of a launch (state +
+            10 command blocks, >= 0.5 GB per GPU even at N = 8) is larger than L2, so no flush is needed.
+  e2e       the same work through the C ABI with HOST buffers, closed loop per command period: H2D of the period's commands
+            from pinned host memory, 30 world-steps, D2H of the per-world event / statistics words -- `e2e` -- or of those
+            plus every pose and velocity (832 B per world, what the reference's loop reads after each step,
+            src/main.c:80-85) -- `e2e.with_state`.  Chunked pipeline: `--e2e-chunks` world ranges per GPU, one stream each.
+  parity    64 sampled worlds of the TIMED batch (global ids k * total/64) are re-run on the CPU oracle through the
+            same schedule and compared bit for bit with the device state after the device arm and after the e2e arm.
+  roofline  algorithmic bytes (1,232 B per 6v6 world-step) / launch duration vs measured HBM bandwidth.
+  cpu_baseline  the CPU oracle (restated-Bullet port; Bullet itself is not buildable here) on the host cores for a
+            bounded sample of the same workload (N = 1, rank 0 only).
+  configs_1 / config_3 / config_4  sub-results at N = 1: BASELINE.json configs[1], [2], [3] at their stated sizes.
 
-`--impl reference` times that CPU oracle alone (rank 0 only) on the same config.
-Multi-GPU: one process per GPU (torchrun), contiguous world ranges, no per-step collective; one
-NCCL all-gather of the episode statistics at the end of the timed region.
+`--impl reference` times that CPU oracle alone (rank 0 only) on a bounded sample of the same workload.
 """
 import argparse
 import ctypes as C
@@ -43,9 +38,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORLD_STEPS_PER_STEP = 30      # commands are redrawn every 30 world-steps
-SETTLE_STEPS = 120             # drop from 0.5 m and settle before timing (2 s of sim time)
+PERIOD_STEPS = 30              # commands are redrawn every 30 world-steps
+PERIODS_PER_STEP = 10          # one bench step = 10 command periods, fused into one launch by the device arm
+WORLD_STEPS_PER_STEP = PERIOD_STEPS * PERIODS_PER_STEP
+SETTLE_STEPS = 120             # drop from 0.5 m and settle before timing (2 s of sim time, command period 0)
+TOTAL_WORLDS = 1 << 20         # 1,048,576 (BASELINE.json configs[4])
 SEED = 0x5351
+N_SAMPLED = 64
 
 
 def bytes_per_world_step(R):
@@ -105,19 +104,10 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(self.period)
 
-    def _sample_once(self):
-        nv = self.nv
-        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-
     def finish(self):
         self._halt.set()
         if self.is_alive():
             self.join(timeout=1.0)
-        if self.ok and not self.samples:   # a very short timed region: the GPU is still at its load clock right after it
-            try:
-                self._sample_once()
-            except Exception:
-                pass
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
@@ -132,83 +122,93 @@ def cpu_oracle_rate(R, sample_worlds, target_seconds, threads):
     period, done, t0 = 1, 0, time.perf_counter()
     while True:
         w.gen_commands(period, 0)
-        w.step(WORLD_STEPS_PER_STEP, threads=threads)
+        w.step(PERIOD_STEPS, threads=threads)
         period += 1
-        done += sample_worlds * WORLD_STEPS_PER_STEP
+        done += sample_worlds * PERIOD_STEPS
         el = time.perf_counter() - t0
         if el >= target_seconds:
             return done / el, el, period - 1
 
 
+def config_dict(args, world_size):
+    per = args.total_worlds // world_size
+    return {"workload": "configs[4]: %d batched 6v6 worlds in total over %d GPU(s) (%d per GPU, contiguous ranges), "
+                        "FIELD_2015, randomized wheel-velocity commands redrawn every %d world-steps; 1 bench step = "
+                        "%d command periods = %d world-steps of every world"
+                        % (args.total_worlds, world_size, per, PERIOD_STEPS, PERIODS_PER_STEP, WORLD_STEPS_PER_STEP),
+            "total_worlds": args.total_worlds, "worlds_per_gpu": per, "robots_per_world": args.robots,
+            "world_steps_per_step": WORLD_STEPS_PER_STEP, "command_periods_per_step": PERIODS_PER_STEP,
+            "substeps_per_world_step": 2,
+            "sharding": "contiguous world ranges, no per-step collective; NCCL all-gather of the episode statistics",
+            "l2": "no flush needed: one launch streams %.0f MiB per GPU (state + %d command blocks) > 126 MB L2"
+                  % (per * (2 * 16 * (args.robots + 1) + 32 + PERIODS_PER_STEP * 32 * args.robots) / 2 ** 20,
+                     PERIODS_PER_STEP)}
+
+
 def run_reference(args, rank, world_size):
     """--impl reference: the reference's CPU implementation of the path on the host cores.
-    Bullet (the reference's step, src/sslsim.cpp:323) cannot be built here, so this is the
-    restated-Bullet CPU oracle (kind "port") with every host thread, on the bench config."""
+    Bullet (the reference's step, src/sslsim.cpp:323) cannot be built here (probe of the GPU box:
+    profiles/r2_bullet_probe.txt), so this is the restated-Bullet CPU oracle (kind "port") with every host thread.
+    Each step is a bounded sample: `--ref-sample-worlds` of the workload's worlds run the step's 300 world-steps;
+    `value` is the measured rate, `ms_per_step` is rescaled to the full workload."""
     if rank != 0:
         return
     import oracle_binding as ob
     ob.build()
     threads = os.cpu_count() or 1
     R = args.robots
-    sample = min(args.worlds, args.ref_sample_worlds)
-    w = ob.Worlds(sample, R, seed=SEED)
+    sample = min(args.total_worlds, args.ref_sample_worlds)
+    ids = [k * (args.total_worlds // sample) for k in range(sample)]
+    w = ob.Worlds(sample, R, seed=SEED, world_ids=ids)
     w.gen_commands(0, 0)
     w.step(SETTLE_STEPS, threads=threads)
+
+    def one_step(k):
+        for j in range(PERIODS_PER_STEP):
+            w.gen_commands(1 + k * PERIODS_PER_STEP + j, 0)
+            w.step(PERIOD_STEPS, threads=threads)
     for k in range(args.warmup):
-        w.gen_commands(1 + k, 0)
-        w.step(WORLD_STEPS_PER_STEP, threads=threads)
+        one_step(k)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        w.gen_commands(1 + args.warmup + k, 0)
-        w.step(WORLD_STEPS_PER_STEP, threads=threads)
+        one_step(args.warmup + k)
     el = time.perf_counter() - t0
     value = sample * WORLD_STEPS_PER_STEP * args.steps / el
+    cfg = config_dict(args, world_size)
+    cfg["reference_sample"] = ("the CPU arm steps %d of the %d worlds (ids k * %d) per bench step and rescales "
+                               "ms_per_step by %d; value is the measured rate" %
+                               (sample, args.total_worlds, args.total_worlds // sample, args.total_worlds // sample))
     line = {
         "impl": "reference", "metric": "world-steps/sec (6v6, 60 Hz)", "value": value, "unit": "world-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": el * 1e3 / args.steps * (args.worlds / sample), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, world_size),
+        "ms_per_step": el * 1e3 / args.steps * (args.total_worlds / sample), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": threads, "kind": "port",
-                         "sample": "%d of %d worlds x %d world-steps per step, %d steps; restated-Bullet CPU oracle "
-                                   "(oracle/ssl_oracle.c), Bullet itself not buildable here" %
-                                   (sample, args.worlds, WORLD_STEPS_PER_STEP, args.steps)},
+                         "sample": "%d of %d worlds x %d world-steps per step, %d steps in %.1f s; restated-Bullet CPU "
+                                   "oracle (oracle/ssl_oracle.c, gcc -O2, pthreads), Bullet itself not buildable here" %
+                                   (sample, args.total_worlds, WORLD_STEPS_PER_STEP, args.steps, el)},
         "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def config_dict(args, world_size):
-    return {"workload": "configs[1]: %d batched %dv%d worlds per GPU, FIELD_2015, randomized wheel-velocity "
-                        "commands redrawn every %d world-steps; 1 bench step = %d world-steps of every world"
-                        % (args.worlds, args.robots // 2, args.robots // 2, WORLD_STEPS_PER_STEP, WORLD_STEPS_PER_STEP),
-            "worlds_per_gpu": args.worlds, "robots_per_world": args.robots,
-            "world_steps_per_step": WORLD_STEPS_PER_STEP, "substeps_per_world_step": 2,
-            "total_worlds": args.worlds * world_size, "sharding": "contiguous world ranges, no per-step collective",
-            "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs); "
-                  "working set %.1f MiB < L2" % (args.worlds * (bytes_per_world_step(args.robots) - 16 + 32) / 2 ** 20)}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU (configs[1]: 4096)")
+    ap.add_argument("--total-worlds", type=int, default=TOTAL_WORLDS, help="worlds in total over all GPUs (configs[4]: 1,048,576)")
     ap.add_argument("--robots", type=int, default=12, help="robots per world (6v6 = 12)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per world: 16, 32 or 0 = auto")
-    ap.add_argument("--ref-sample-worlds", type=int, default=512)
+    ap.add_argument("--ref-sample-worlds", type=int, default=2048)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8,
-                    help="e2e arm: chunks of worlds, each on its own stream (1 = whole batch, one barrier per step)")
-    ap.add_argument("--periods-per-launch", type=int, default=10,
-                    help="device-resident arm: command periods (bench steps) fused into one step_worlds launch")
-    ap.add_argument("--large-worlds", type=int, default=131072,
-                    help="extra measurement at this many worlds per GPU (0 = skip); not the headline value")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-sub-results", action="store_true", help="skip the configs[1], [2], [3] sub-results (N = 1 only anyway)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="e2e arm: chunks of worlds per GPU, each on its own stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -237,23 +237,20 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    W, R, K, WU = args.worlds, args.robots, args.steps, args.warmup
-    N = R + 1
+    R, K, WU, PPS = args.robots, args.steps, args.warmup, PERIODS_PER_STEP
+    TOTAL = args.total_worlds
     bpws = bytes_per_world_step(R)
-    first_world, _ = sim.shard_range(W * world_size, rank, world_size)   # contiguous range per GPU
+    first_world, W = sim.shard_range(TOTAL, rank, world_size)   # this GPU's contiguous range
+    L = sim.lib()
     b = sim.WorldBatch(W, R, device=local_rank, seed=SEED, first_world_id=first_world)
     if args.lanes:
         b.set_lanes_per_world(args.lanes)
-    # stage every command batch (warm-up + timed) in HBM before the timed region
     cmd_bytes = W * R * 32
-    n_sets = WU + K
-    stage = torch.empty(n_sets * cmd_bytes, dtype=torch.uint8, device=dev)
-    for k in range(n_sets):
-        b.gen_commands_into(stage.data_ptr() + k * cmd_bytes, 1 + k, 0)
-    b.gen_commands(0, 0)
-    b.step(SETTLE_STEPS)
-    b.sync()
-    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    stage = torch.empty(PPS * cmd_bytes, dtype=torch.uint8, device=dev)   # the command blocks of one bench step
+
+    def gen_step(k):   # device-side synthetic command stream: periods 1 + k*PPS ... of the keyed generator
+        for j in range(PPS):
+            b.gen_commands_into(stage.data_ptr() + j * cmd_bytes, 1 + k * PPS + j, 0)
 
     def barrier():
         b.sync()
@@ -266,161 +263,183 @@ def main():
         _, tot = sim.allgather_stats(b.reduce_stats(), device=dev)
         return tot
 
-    # ---- device-resident arm ------------------------------------------------------------------
-    for k in range(WU):
-        b.set_commands_device(stage.data_ptr() + k * cmd_bytes)
-        b.step(WORLD_STEPS_PER_STEP)
-        flush.zero_()
-    allgather_stats()  # warms the NCCL communicator up
-    torch.cuda.synchronize()
-    def device_arm(periods_per_launch, sample_clocks):
-        """K bench steps, `periods_per_launch` of them per step_worlds launch (the staged command blocks are
-        consecutive in HBM); CUDA events bracket every launch on the batch's stream, L2 flushed in between."""
-        b.enable_kernel_timing(True)
-        b.kernel_time(reset=True)
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        barrier()
-        if sampler:
-            sampler.start()
-        t0 = time.perf_counter()
-        k = 0
-        while k < K:
-            p = min(periods_per_launch, K - k)
-            b.step_sequence_device(stage.data_ptr() + (WU + k) * cmd_bytes, p, WORLD_STEPS_PER_STEP)
-            b.sync()
-            flush.zero_()                   # L2 flush, outside the event pair
-            torch.cuda.synchronize()
-            k += p
-        stats = allgather_stats()
-        barrier()
-        wall = time.perf_counter() - t0
-        clk = sampler.finish() if sampler else None
-        ms, n = b.kernel_time(reset=True)
-        b.enable_kernel_timing(False)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+    def allmax(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
         if distributed:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), n, clk, stats
+        return [float(v) for v in t]
 
-    PPL = max(1, args.periods_per_launch)
-    snap = b.snapshot()
-    kern_ms_max, wall_ms_max, launches, clocks, total_stats = device_arm(PPL, True)
-    single = None
-    if PPL > 1:     # the same K steps again, one launch per command period (what a closed-loop caller does)
-        b.restore(snap)
-        ms1, _, n1, _, stats1 = device_arm(1, False)
-        assert stats1 == total_stats, "fused and per-period launches must produce identical worlds"
-        single = {"value": W * world_size * WORLD_STEPS_PER_STEP * K / (ms1 * 1e-3), "ms_per_step": ms1 / K,
-                  "launches": n1}
-    b.free_snapshot(snap)
-    units = W * world_size * WORLD_STEPS_PER_STEP * K
+    # ---- sampled worlds for the in-run parity check (global ids k * TOTAL/64; this rank checks the ones it owns)
+    stride = max(1, TOTAL // N_SAMPLED)
+    sampled = [g for g in range(0, TOTAL, stride)][:N_SAMPLED]
+    mine = [g for g in sampled if first_world <= g < first_world + W]
+    local_ids = [g - first_world for g in mine]
+
+    # ---- settle + warm-up (device arm) ---------------------------------------------------------------------
+    b.gen_commands(0, 0)
+    b.step(SETTLE_STEPS)
+    for k in range(WU):
+        gen_step(k)
+        b.step_sequence_device(stage.data_ptr(), PPS, PERIOD_STEPS)
+    allgather_stats()  # warms the NCCL communicator up
+    snap = b.snapshot()   # state after settle + warm-up: the e2e arms start here too
+
+    # ---- device-resident arm -----------------------------------------------------------------------------
+    b.enable_kernel_timing(True)
+    b.kernel_time(reset=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for k in range(K):
+        gen_step(WU + k)                                                   # untimed: outside the event pair
+        b.step_sequence_device(stage.data_ptr(), PPS, PERIOD_STEPS)        # timed: CUDA events around the launch
+    total_stats = allgather_stats()
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.finish()
+    kern_ms, launches = b.kernel_time(reset=True)
+    b.enable_kernel_timing(False)
+    kern_ms_max, wall_ms_max = allmax(kern_ms, wall_s * 1e3)
+    per_rank_ms = [kern_ms]
+    if distributed:
+        tl = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world_size)]
+        dist.all_gather(tl, torch.tensor([kern_ms], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(t[0]) for t in tl]
+    units = TOTAL * WORLD_STEPS_PER_STEP * K
     value = units / (kern_ms_max * 1e-3)
+    dev_state = b.read_worlds(local_ids) if local_ids else None
 
-    # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
-    e2e = None
+    # ---- end-to-end arms: host buffers through the C ABI ------------------------------------------------------------
+    e2e, e2e_state = None, None
+    N_HOST = 2
     if not args.no_e2e:
-        n_host = min(n_sets, 16)
-        host_cmd = torch.empty(n_host * cmd_bytes, dtype=torch.uint8).pin_memory()
-        host_cmd.copy_(stage[: n_host * cmd_bytes].cpu())
-        host_aux = torch.empty(W * 8, dtype=torch.int32).pin_memory()
-        hp, ap_ = host_cmd.data_ptr(), host_aux.data_ptr()
-        L, h = sim.lib(), b._h
-
-        def whole_step(k):
-            L.world_batch_set_commands(h, C.c_void_p(hp + (k % n_host) * cmd_bytes))   # H2D, pinned
-            L.world_batch_step(h, WORLD_STEPS_PER_STEP)
-            rc = L.world_batch_read_aux(h, C.c_void_p(ap_))                            # D2H + sync
-            if rc < 0:
-                raise RuntimeError("e2e step failed: %d" % rc)
-
-        def timed(step_fn):
-            for k in range(WU):
-                step_fn(k)
-            barrier()
-            t0 = time.perf_counter()
-            for k in range(K):
-                step_fn(WU + k)
-            barrier()                      # every chunk's last results are in host memory
-            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if distributed:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            return float(te[0])
-
-        snap = b.snapshot()
-        whole_s = timed(whole_step)
-        e2e_s, api = whole_s, "world_batch_set_commands(host) + world_batch_step(30) + world_batch_read_aux(host)"
         nch = max(1, min(args.e2e_chunks, W))
-        if nch > 1:
-            stats_whole = b.reduce_stats()
+        host_cmd = torch.empty(N_HOST * cmd_bytes, dtype=torch.uint8).pin_memory()
+        for s in range(N_HOST):   # host command sets = generator periods 100000 + s (copied out once, untimed)
+            b.gen_commands_into(stage.data_ptr(), 100000 + s, 0)
+            b.sync()
+            host_cmd[s * cmd_bytes:(s + 1) * cmd_bytes].copy_(stage[:cmd_bytes])
+        torch.cuda.synchronize()
+        host_aux = torch.empty(W * 8, dtype=torch.int32).pin_memory()
+        host_pos = torch.empty(W * (R + 1) * 4, dtype=torch.float32).pin_memory()
+        host_vel = torch.empty(W * (R + 1) * 4, dtype=torch.float32).pin_memory()
+        hp, ap_, pp, vp = host_cmd.data_ptr(), host_aux.data_ptr(), host_pos.data_ptr(), host_vel.data_ptr()
+        h = b._h
+        NB = (R + 1) * 16
+
+        def run_e2e(with_state):
             b.restore(snap)
             b.set_chunks(nch)
             ranges = [b.chunk_range(c) for c in range(nch)]
+            counter = [0]
 
-            def chunk_step(k):
-                base = hp + (k % n_host) * cmd_bytes
+            def period():
+                base = hp + (counter[0] % N_HOST) * cmd_bytes
+                counter[0] += 1
                 for c, (first, count) in enumerate(ranges):
-                    # closed loop: this chunk's results of the previous step are in host memory before its next
+                    # closed loop: this chunk's results of the previous period are in host memory before its next
                     # commands are submitted; the other chunks' queued work overlaps the wait
-                    if L.world_batch_chunk_wait(h, c) < 0 or L.world_batch_chunk_step(
-                            h, c, C.c_void_p(base + first * R * 32), WORLD_STEPS_PER_STEP,
-                            C.c_void_p(ap_ + first * 32)) < 0:
-                        raise RuntimeError("e2e chunk step failed")
-            e2e_s = timed(chunk_step)
-            assert b.reduce_stats() == stats_whole, "chunked and whole-batch stepping must produce identical worlds"
+                    rc = L.world_batch_chunk_wait(h, c)
+                    if rc >= 0:
+                        rc = L.world_batch_chunk_step_ex(
+                            h, c, C.c_void_p(base + first * R * 32), PERIOD_STEPS, C.c_void_p(ap_ + first * 32),
+                            C.c_void_p(pp + first * NB) if with_state else None,
+                            C.c_void_p(vp + first * NB) if with_state else None)
+                    if rc < 0:
+                        raise RuntimeError("e2e chunk step failed: %d" % rc)
+            for _ in range(WU * PPS):
+                period()
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(K * PPS):
+                period()
+            barrier()                      # every chunk's last results are in host memory
+            el = allmax(time.perf_counter() - t1)[0]
+            st = b.reduce_stats()
+            state = b.read_worlds(local_ids) if local_ids else None
             b.set_chunks(0)
-            api = ("%d chunks x [world_batch_chunk_wait + world_batch_chunk_step(host commands, 30, host aux)], "
-                   "one CUDA stream per chunk" % nch)
-        b.free_snapshot(snap)
-        e2e = {"value": units / e2e_s, "unit": "world-steps/s", "h2d_bytes_per_step": cmd_bytes,
-               "d2h_bytes_per_step": W * 32, "ms_per_step": e2e_s * 1e3 / K, "chunks": nch, "api": api,
-               "whole_batch": {"value": units / whole_s, "ms_per_step": whole_s * 1e3 / K,
-                               "api": "world_batch_set_commands(host) + world_batch_step(30) + "
-                                      "world_batch_read_aux(host), one barrier per step"}}
+            return el, st, state
 
-    # ---- extra: the per-GPU shard of configs[4] (1,048,576 worlds over 8 GPUs = 131,072 per GPU) ---------------
-    large = None
-    if args.large_worlds > 0:
-        WL, KL = args.large_worlds, 8
-        first_l, _ = sim.shard_range(WL * world_size, rank, world_size)
-        bl = sim.WorldBatch(WL, R, device=local_rank, seed=SEED, first_world_id=first_l)
-        bl.gen_commands(0, 0)
-        bl.step(SETTLE_STEPS)
-        for k in range(3):
-            bl.gen_commands(1 + k, 0)
-            bl.step(WORLD_STEPS_PER_STEP)
-        stage_l = torch.empty(KL * WL * R * 32, dtype=torch.uint8, device=dev)
-        for k in range(KL):
-            bl.gen_commands_into(stage_l.data_ptr() + k * WL * R * 32, 4 + k, 0)
-        bl.sync()
-        bl.enable_kernel_timing(True)
-        bl.kernel_time(reset=True)
-        barrier()
-        bl.step_sequence_device(stage_l.data_ptr(), KL, WORLD_STEPS_PER_STEP)   # the KL periods in one launch
-        ms_l, n_l = bl.kernel_time(reset=True)
-        tl = torch.tensor([ms_l], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-        v_l = WL * world_size * WORLD_STEPS_PER_STEP * KL / (float(tl[0]) * 1e-3)
-        large = {"workload": "configs[4] shard: %d 6v6 worlds per GPU, same command stream, %d command periods "
-                             "in one timed launch (working set %.0f MiB > L2 at 131,072)"
-                             % (WL, KL, WL * (bpws - 16 + 32) / 2 ** 20),
-                 "value": v_l, "unit": "world-steps/s", "ms_per_step": float(tl[0]) / KL,
-                 "roofline_frac": (bpws * WL * WORLD_STEPS_PER_STEP) / (float(tl[0]) / KL * 1e-3) / 1e9 / measured_peak()[0]}
-        bl.close()
+        e_s, e_stats, e2e_state = run_e2e(False)
+        s_s, s_stats, _ = run_e2e(True)
+        assert s_stats == e_stats, "the two e2e variants must produce identical worlds"
+        api = ("%d chunks per GPU x [world_batch_chunk_wait + world_batch_chunk_step_ex(host commands, %d steps, host aux%s)], "
+               "one CUDA stream per chunk, per command period")
+        e2e = {"value": units / e_s, "unit": "world-steps/s",
+               "h2d_bytes_per_step": PPS * cmd_bytes * world_size, "d2h_bytes_per_step": PPS * W * 32 * world_size,
+               "ms_per_step": e_s * 1e3 / K, "chunks": nch, "api": api % (nch, PERIOD_STEPS, ""),
+               "with_state": {"value": units / s_s, "unit": "world-steps/s", "ms_per_step": s_s * 1e3 / K,
+                              "h2d_bytes_per_step": PPS * cmd_bytes * world_size,
+                              "d2h_bytes_per_step": PPS * W * (32 + 2 * NB) * world_size,
+                              "api": api % (nch, PERIOD_STEPS, ", host pos, host vel"),
+                              "note": "every pose and velocity read back each command period (832 B per world), as the "
+                                      "reference's loop does after each step (src/main.c:80-85)"}}
+        del host_cmd, host_aux, host_pos, host_vel
+    b.free_snapshot(snap)
 
-    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+    # ---- in-run parity: the sampled worlds of the timed batch on the CPU oracle ---------------------------------------
+    parity = None
+    if not args.no_parity:
+        import oracle_binding as ob
+        ob.build()
         threads = os.cpu_count() or 1
-        v, el, reps = cpu_oracle_rate(R, min(W, args.ref_sample_worlds), args.cpu_seconds, threads)
-        cpu = {"value": v, "unit": "world-steps/s", "cores": threads, "kind": "port",
-               "sample": "%d worlds x %d world-steps x %d command batches in %.1f s; restated-Bullet CPU oracle "
-                         "(oracle/ssl_oracle.c, -O2, pthreads); Bullet itself is not buildable here (SURVEY 8c)"
-                         % (min(W, args.ref_sample_worlds), WORLD_STEPS_PER_STEP, reps, el)}
+        bad_dev = bad_e2e = skipped = 0
+        if mine:
+            o = ob.Worlds(len(mine), R, seed=SEED, world_ids=mine)
+            o.gen_commands(0, 0)
+            o.step(SETTLE_STEPS, threads=threads)
+            for p in range(WU * PPS):
+                o.gen_commands(1 + p, 0)
+                o.step(PERIOD_STEPS, threads=threads)
+            warm = (o.pos.copy(), o.vel.copy(), o.aux.copy())
+            for p in range(WU * PPS, (WU + K) * PPS):
+                o.gen_commands(1 + p, 0)
+                o.step(PERIOD_STEPS, threads=threads)
+            ok_rows = ((o.aux[:, 0] >> 16) & 1) == 0          # overflowed worlds: state unspecified (STEP_SPEC 4.3)
+            skipped = int((~ok_rows).sum())
+            same = [all(np.array_equal(a[i], g[i]) for a, g in zip((o.pos, o.vel, o.aux), dev_state)) for i in range(len(mine))]
+            bad_dev = sum(1 for i, s in enumerate(same) if ok_rows[i] and not s)
+            if e2e_state is not None:
+                o.pos[:], o.vel[:], o.aux[:] = warm
+                for p in range((WU + K) * PPS):
+                    o.gen_commands(100000 + p % N_HOST, 0)
+                    o.step(PERIOD_STEPS, threads=threads)
+                same = [all(np.array_equal(a[i], g[i]) for a, g in zip((o.pos, o.vel, o.aux), e2e_state)) for i in range(len(mine))]
+                ok2 = ((o.aux[:, 0] >> 16) & 1) == 0
+                bad_e2e = sum(1 for i, s in enumerate(same) if ok2[i] and not s)
+        t = torch.tensor([bad_dev, bad_e2e, skipped, len(mine)], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        bad_dev, bad_e2e, skipped, n_checked = (int(v) for v in t)
+        parity = {"worlds": n_checked, "bit_exact": bad_dev == 0 and bad_e2e == 0, "mismatching_device_arm": bad_dev,
+                  "mismatching_e2e_arm": bad_e2e if e2e is not None else None, "overflowed_skipped": skipped,
+                  "world_steps_checked_per_world": SETTLE_STEPS + (WU + K) * WORLD_STEPS_PER_STEP,
+                  "against": "oracle/ssl_oracle.c (restated Bullet 2.82 step, parity unpinned against Bullet itself)",
+                  "sampled_ids": "k * %d, k = 0..%d" % (stride, len(sampled) - 1)}
+
+    # ---- sub-results and CPU baseline (N = 1, rank 0) ---------------------------------------------------------------------
+    b.close()
+    del stage
+    subs = {}
+    cpu = None
+    if rank == 0 and world_size == 1:
+        if not args.no_sub_results:
+            import bench_configs
+            subs = bench_configs.run_all(sim, dev, local_rank, SEED, check_parity=not args.no_parity)
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sw = min(TOTAL, args.ref_sample_worlds)
+            v, el, reps = cpu_oracle_rate(R, sw, args.cpu_seconds, threads)
+            cpu = {"value": v, "unit": "world-steps/s", "cores": threads, "kind": "port",
+                   "sample": "%d worlds x %d world-steps x %d command periods in %.1f s; restated-Bullet CPU oracle "
+                             "(oracle/ssl_oracle.c, gcc -O2, pthreads); Bullet itself is not buildable here (SURVEY 8c)"
+                             % (sw, PERIOD_STEPS, reps, el)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        per_launch_bytes = bpws * W * WORLD_STEPS_PER_STEP * K / launches
+        slow = max(range(world_size), key=lambda r: per_rank_ms[r])
+        per_launch_bytes = bpws * W * WORLD_STEPS_PER_STEP
         per_launch_s = kern_ms_max * 1e-3 / launches
         achieved = per_launch_bytes / per_launch_s / 1e9
         traffic, issue = None, None
@@ -429,40 +448,39 @@ def main():
             try:
                 with open(tp) as f:
                     tj = json.load(f)
-                traffic = tj.get("dram_bytes_per_launch")
-                # secondary ceiling: the kernel is issue/latency-bound, so also report warp-instructions issued per
-                # second against 148 SMs x 4 schedulers x SM clock (instruction count per world-step from the
-                # committed ncu capture of the 4096-world launch)
-                ipw = tj["warp_instructions_per_launch"] / tj.get("world_steps_per_launch", 4096 * WORLD_STEPS_PER_STEP)
-                if traffic is not None:   # scale the captured launch to this run's launch shape
-                    traffic = traffic * (W * WORLD_STEPS_PER_STEP * K / launches) / tj.get("world_steps_per_launch", 1)
+                wsl = float(tj["world_steps_per_launch"])
+                traffic = tj["dram_bytes_per_launch"] * (W * WORLD_STEPS_PER_STEP) / wsl   # scaled to this launch shape
+                ipw = tj["warp_instructions_per_launch"] / wsl
                 peak_issue = 148 * 4 * (clocks.get("sm_max_mhz") or 1965) * 1e6
                 issue = {"warp_instructions_per_world_step": ipw, "achieved_per_s": ipw * value / world_size,
                          "peak_per_s": peak_issue, "frac": ipw * value / world_size / peak_issue,
-                         "source": "profiles/traffic.json (ncu smsp__inst_executed.sum)"}
+                         "source": "profiles/traffic.json (ncu smsp__inst_executed.sum of %s)" % tj.get("capture", "the committed capture")}
             except Exception:
                 traffic = None
         line = {
             "metric": "world-steps/sec (6v6, 60 Hz)", "value": value, "unit": "world-steps/s",
             "n_gpus": world_size, "steps": K, "warmup": WU, "ms_per_step": kern_ms_max / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, world_size),
-            "wall_ms_per_step_incl_l2_flush": wall_ms_max / K,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches + 1,
-            "periods_per_launch": PPL, "one_launch_per_period": single,
+            "timed_region_s": kern_ms_max * 1e-3, "wall_ms_per_step_incl_command_generation": wall_ms_max / K,
+            "clocks": clocks, "e2e": e2e, "parity": parity,
+            "gpu_launches": launches + K * PPS + 1,
+            "gpu_launches_detail": {"step_worlds": launches, "gen_commands": K * PPS, "reduce_stats": 1},
+            "per_rank_kernel_ms": {"min": min(per_rank_ms), "median": statistics.median(per_rank_ms),
+                                   "max": max(per_rank_ms), "slowest_rank": slow, "all": per_rank_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "step_worlds", "algorithmic_bytes_per_launch": per_launch_bytes,
-                         "bytes_per_world_step": bpws, "kernel_ms_per_launch": kern_ms_max / launches, "issue_ceiling": issue,
-                         "note": "latency/issue-bound fused kernel: state stays in registers for all "
-                                 "world-steps of a launch (DRAM traffic = state once + one command block per "
-                                 "period); issue_ceiling is the informative bound; see DESIGN.md"},
+                         "bytes_per_world_step": bpws, "world_steps_per_launch": W * WORLD_STEPS_PER_STEP,
+                         "kernel_ms_per_launch": kern_ms_max / launches, "issue_ceiling": issue,
+                         "note": "latency/issue-bound fused kernel: state stays in registers for the 300 world-steps of "
+                                 "a launch (DRAM traffic = state once + one command block per period); issue_ceiling "
+                                 "is the informative bound; see DESIGN.md"},
             "cpu_baseline": cpu,
-            "large_batch": large,
             "episode_stats": total_stats,
         }
+        line.update(subs)
         print(json.dumps(line), flush=True)
-    b.close()
     if distributed:
         dist.destroy_process_group()
     return 0

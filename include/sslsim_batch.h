@@ -157,6 +157,15 @@ int world_batch_chunk_count(const struct WorldBatch *batch);
 int world_batch_chunk_range(const struct WorldBatch *batch, int chunk, int *first_world, int *n_worlds);
 int world_batch_chunk_step(struct WorldBatch *batch, int chunk, const struct RobotCommand *host_cmds, int n_steps,
                            uint32_t *host_aux);
+/* the same with the chunk's full state copied back as well (the reference's loop reads every pose after every step,
+ * src/main.c:80-85): host_pos / host_vel [chunk worlds][n_robots + 1][4] floats, NULL to skip */
+int world_batch_chunk_step_ex(struct WorldBatch *batch, int chunk, const struct RobotCommand *host_cmds, int n_steps,
+                              uint32_t *host_aux, float *host_pos, float *host_vel);
+/* a command sequence (world_batch_step_sequence's layout: n_periods blocks of the whole batch's [n_worlds][n_robots]
+ * records, device memory) for one chunk, on the chunk's stream; chunks submitted back to back overlap, which fills
+ * the tail of small batches (a launch ends with its slowest world) */
+int world_batch_chunk_step_sequence(struct WorldBatch *batch, int chunk, const struct RobotCommand *dev_cmds,
+                                    int n_periods, int steps_per_period);
 int world_batch_chunk_wait(struct WorldBatch *batch, int chunk);
 
 /* ---- command input (no upstream implementation; schema grSim_Commands.proto).
@@ -183,6 +192,8 @@ int world_batch_replace_balls(struct WorldBatch *batch, const struct BallReplace
 int world_batch_read_state(struct WorldBatch *batch, float *pos, float *vel, uint32_t *aux);
 int world_batch_write_state(struct WorldBatch *batch, const float *pos, const float *vel, const uint32_t *aux);
 int world_batch_read_aux(struct WorldBatch *batch, uint32_t *aux);
+/* selected worlds only: pos/vel [n][n_robots + 1][4] floats, aux [n][8] words (bulk form of the per-world getters) */
+int world_batch_read_worlds(struct WorldBatch *batch, const int *world_ids, int n, float *pos, float *vel, uint32_t *aux);
 /* zero-copy: device pointers of the live buffers (pos/vel: float4 [W][R+1];
  * aux: u32 [W][8]; cmd: RobotCommand [W][R] or NULL) */
 int world_batch_device_state(struct WorldBatch *batch, void **pos, void **vel, void **aux, void **cmd);

@@ -114,6 +114,9 @@ BATCH_SYMBOLS = [
     ("world_batch_set_chunks", _I, [_VP, _I]), ("world_batch_chunk_count", _I, [_VP]),
     ("world_batch_chunk_range", _I, [_VP, _I, C.POINTER(_I), C.POINTER(_I)]),
     ("world_batch_chunk_step", _I, [_VP, _I, _VP, _I, _VP]), ("world_batch_chunk_wait", _I, [_VP, _I]),
+    ("world_batch_chunk_step_ex", _I, [_VP, _I, _VP, _I, _VP, _VP, _VP]),
+    ("world_batch_chunk_step_sequence", _I, [_VP, _I, _VP, _I, _I]),
+    ("world_batch_read_worlds", _I, [_VP, _VP, _I, _VP, _VP, _VP]),
     ("world_batch_step_sequence", _I, [_VP, _VP, _I, _I]), ("world_batch_step_sequence_host", _I, [_VP, _VP, _I, _I]),
     ("world_batch_set_commands", _I, [_VP, _VP]), ("world_batch_set_commands_device", _I, [_VP, _VP]),
     ("world_batch_clear_commands", _I, [_VP]), ("world_batch_gen_commands", _I, [_VP, _U64, _I]),
@@ -287,6 +290,18 @@ class WorldBatch:
     def chunk_step(self, chunk, host_cmd_ptr, n_steps, host_aux_ptr):
         """queue H2D(commands of the chunk) + n_steps + D2H(aux of the chunk) on the chunk's stream; returns at once"""
         self._ck(lib().world_batch_chunk_step(self._h, chunk, host_cmd_ptr, n_steps, host_aux_ptr))
+
+    def chunk_step_sequence(self, chunk, dev_ptr, n_periods, steps_per_period):
+        self._ck(lib().world_batch_chunk_step_sequence(self._h, chunk, C.c_void_p(dev_ptr), n_periods, steps_per_period))
+
+    def read_worlds(self, ids):
+        """state of selected worlds: (pos [n, N, 4], vel [n, N, 4], aux [n, 8])"""
+        ids = np.ascontiguousarray(ids, np.int32)
+        pos = np.empty((ids.size, self.N, 4), np.float32)
+        vel = np.empty_like(pos)
+        aux = np.empty((ids.size, 8), np.uint32)
+        self._ck(lib().world_batch_read_worlds(self._h, _ptr(ids), ids.size, _ptr(pos), _ptr(vel), _ptr(aux)))
+        return pos, vel, aux
 
     def chunk_wait(self, chunk):
         self._ck(lib().world_batch_chunk_wait(self._h, chunk))

@@ -330,6 +330,43 @@ int world_batch_chunk_step(struct WorldBatch *b, int chunk, const struct RobotCo
   return SSLSIM_OK;
 }
 
+/* chunk_step with the full state read back: what the reference's loop does after every step (src/main.c:80-85 reads
+ * every pose for the detection packet).  host_pos / host_vel: [chunk worlds][n_robots + 1][4] floats, may be NULL. */
+int world_batch_chunk_step_ex(struct WorldBatch *b, int chunk, const struct RobotCommand *host_cmds, int n_steps,
+                              uint32_t *host_aux, float *host_pos, float *host_vel) {
+  const int rc = world_batch_chunk_step(b, chunk, host_cmds, n_steps, host_aux);
+  if (rc != SSLSIM_OK) return rc;
+  WorldBatch::Chunk &k = b->chunks[chunk];
+  const size_t N = (size_t)b->R + 1, off = (size_t)k.first * N, nb = (size_t)k.count * N * sizeof(float4);
+  if (host_pos) CK(cudaMemcpyAsync(host_pos, b->d_pos + off, nb, cudaMemcpyDeviceToHost, k.stream));
+  if (host_vel) CK(cudaMemcpyAsync(host_vel, b->d_vel + off, nb, cudaMemcpyDeviceToHost, k.stream));
+  return SSLSIM_OK;
+}
+
+/* A command sequence for one chunk, on the chunk's stream: dev_cmds holds n_periods blocks of the WHOLE batch's
+ * [n_worlds][n_robots] records (the layout of world_batch_step_sequence); the chunk reads its own rows of every block.
+ * Chunks submitted one after the other run concurrently, so the slow worlds at the end of one chunk's launch overlap
+ * the next chunk's work instead of idling the GPU (small batches: the launch ends with its slowest world). */
+int world_batch_chunk_step_sequence(struct WorldBatch *b, int chunk, const struct RobotCommand *dev_cmds, int n_periods,
+                                    int steps_per_period) {
+  ENTER_NOJOIN(b);
+  if (chunk < 0 || chunk >= (int)b->chunks.size() || !dev_cmds || n_periods <= 0 || steps_per_period <= 0)
+    return SSLSIM_E_ARG;
+  WorldBatch::Chunk &k = b->chunks[chunk];
+  CK(cudaEventRecord(b->ev_main, b->stream));
+  CK(cudaStreamWaitEvent(k.stream, b->ev_main, 0));
+  const long long stride = (long long)b->W * b->R;
+  const StepArgs a = step_args(b, k.first, k.count, dev_cmds, n_periods * steps_per_period, 2, (float)(1.0 / 60 / 2),
+                               steps_per_period, stride);
+  CK(sslsim_launch_step(a, b->lanes, k.stream));
+  k.dirty = true;
+  b->cmd_active = dev_cmds + (size_t)(n_periods - 1) * stride;
+  if (chunk == 0)
+    for (int s = 0; s < n_periods * steps_per_period; ++s) { b->timestamp += (float)(1.0 / 60); b->frame++; }
+  for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
 int world_batch_chunk_wait(struct WorldBatch *b, int chunk) {
   ENTER_NOJOIN(b);
   if (chunk < 0 || chunk >= (int)b->chunks.size()) return SSLSIM_E_ARG;
@@ -429,6 +466,22 @@ int world_batch_read_state(struct WorldBatch *b, float *pos, float *vel, uint32_
   if (pos) CK(cudaMemcpyAsync(pos, b->d_pos, nb, cudaMemcpyDeviceToHost, b->stream));
   if (vel) CK(cudaMemcpyAsync(vel, b->d_vel, nb, cudaMemcpyDeviceToHost, b->stream));
   if (aux) CK(cudaMemcpyAsync(aux, b->d_aux, (size_t)b->W * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return SSLSIM_OK;
+}
+
+/* bulk readout of selected worlds: pos/vel [n][n_robots + 1][4], aux [n][8]; any pointer may be NULL */
+int world_batch_read_worlds(struct WorldBatch *b, const int *world_ids, int n, float *pos, float *vel, uint32_t *aux) {
+  ENTER(b);
+  if (n < 0 || (n > 0 && !world_ids)) return SSLSIM_E_ARG;
+  const size_t N = (size_t)b->R + 1;
+  for (int i = 0; i < n; ++i) {
+    const int w = world_ids[i];
+    if (w < 0 || w >= b->W) return SSLSIM_E_ARG;
+    if (pos) CK(cudaMemcpyAsync(pos + (size_t)i * N * 4, b->d_pos + (size_t)w * N, N * sizeof(float4), cudaMemcpyDeviceToHost, b->stream));
+    if (vel) CK(cudaMemcpyAsync(vel + (size_t)i * N * 4, b->d_vel + (size_t)w * N, N * sizeof(float4), cudaMemcpyDeviceToHost, b->stream));
+    if (aux) CK(cudaMemcpyAsync(aux + (size_t)i * 8, b->d_aux + (size_t)w * 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+  }
   CK(cudaStreamSynchronize(b->stream));
   return SSLSIM_OK;
 }

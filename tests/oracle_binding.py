@@ -48,10 +48,22 @@ def build():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
 
 
+def _cpu_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("flags"):
+                    return " fma " in ln + " "
+    except OSError:
+        pass
+    return False
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(ORACLE_DIR, "libssl_oracle.so")
+        name = "libssl_oracle.so" if _cpu_has_fma() else "libssl_oracle_nofma.so"   # same results, see oracle/Makefile
+        path = os.path.join(ORACLE_DIR, name)
         if not os.path.exists(path):
             build()
         L = C.CDLL(path)
@@ -101,8 +113,11 @@ def _ptr(a):
 class Worlds:
     """W independent oracle worlds, world-major arrays pos/vel [W, R+1, 4], aux [W, 8], cmd [W, R]."""
 
-    def __init__(self, n_worlds, n_robots, fld=FIELD_2015, params=None, seed=0x5351, mode=0, world0=0):
+    def __init__(self, n_worlds, n_robots, fld=FIELD_2015, params=None, seed=0x5351, mode=0, world0=0, world_ids=None):
+        """world_ids: explicit global world ids (sampled worlds of a larger batch); default world0, world0+1, ..."""
         self.W, self.R = n_worlds, n_robots
+        self.ids = [world0 + w for w in range(n_worlds)] if world_ids is None else [int(i) for i in world_ids]
+        assert len(self.ids) == n_worlds
         self.field = field(fld)
         self.params = params if params is not None else default_params()
         self.pos = np.zeros((n_worlds, n_robots + 1, 4), np.float32)
@@ -112,7 +127,7 @@ class Worlds:
         self.seed, self.world0 = seed, world0
         L = lib()
         for w in range(n_worlds):
-            L.orc_init_world(C.byref(self.field), n_robots, seed, world0 + w, mode,
+            L.orc_init_world(C.byref(self.field), n_robots, seed, self.ids[w], mode,
                              _ptr(self.pos[w]), _ptr(self.vel[w]), _ptr(self.aux[w]))
 
     def gen_commands(self, period, kind=0):
@@ -120,7 +135,7 @@ class Worlds:
             self.cmd = np.zeros((self.W, self.R), CMD_DTYPE)
         L = lib()
         for w in range(self.W):
-            L.orc_gen_commands(self.R, self.seed, self.world0 + w, period, kind, _ptr(self.cmd[w]))
+            L.orc_gen_commands(self.R, self.seed, self.ids[w], period, kind, _ptr(self.cmd[w]))
 
     def step(self, n_steps=1, substeps=2, h=H, threads=1):
         lib().orc_step_many(C.byref(self.field), C.byref(self.params), self.R, self.W, _ptr(self.pos),
