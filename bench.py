@@ -242,7 +242,17 @@ def main():
     bpws = bytes_per_world_step(R)
     first_world, W = sim.shard_range(TOTAL, rank, world_size)   # this GPU's contiguous range
     L = sim.lib()
-    b = sim.WorldBatch(W, R, device=local_rank, seed=SEED, first_world_id=first_world)
+    # one process per GPU through the C ABI's multi-GPU layer (include/sslsim_multi.h): rank 0's ncclUniqueId reaches the
+    # other ranks over torch.distributed (plumbing); the shard, its step and the ncclAllGather of the episode statistics
+    # are the library's own
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(sim.WorldMulti.unique_id()), dtype=torch.uint8))
+    if distributed:
+        dist.broadcast(uid, 0)
+    multi = sim.WorldMulti(TOTAL, R, rank=rank, n_ranks=world_size, device=local_rank, nccl_id=bytes(uid.cpu().numpy()), seed=SEED)
+    b = multi.shard(0, seed=SEED)
+    assert (b.W, b.first_world_id) == (W, first_world)
     if args.lanes:
         b.set_lanes_per_world(args.lanes)
     cmd_bytes = W * R * 32
@@ -260,7 +270,7 @@ def main():
             torch.cuda.synchronize()
 
     def allgather_stats():
-        _, tot = sim.allgather_stats(b.reduce_stats(), device=dev)
+        _, tot = multi.allgather_stats()     # K4 on the device + ncclAllGather inside the library
         return tot
 
     def allmax(*vals):
@@ -419,7 +429,9 @@ def main():
                   "sampled_ids": "k * %d, k = 0..%d" % (stride, len(sampled) - 1)}
 
     # ---- sub-results and CPU baseline (N = 1, rank 0) ---------------------------------------------------------------------
+    nccl_version = L.sslsim_multi_nccl_version().decode()
     b.close()
+    multi.close()
     del stage
     subs = {}
     cpu = None
@@ -478,6 +490,8 @@ def main():
                                  "is the informative bound; see DESIGN.md"},
             "cpu_baseline": cpu,
             "episode_stats": total_stats,
+            "multi_gpu": {"api": "include/sslsim_multi.h: new_world_multi_rank + world_multi_allgather_stats (ncclAllGather of "
+                                 "8 x u64 per GPU, once per arm), no per-step collective", "nccl": nccl_version},
         }
         line.update(subs)
         print(json.dumps(line), flush=True)

@@ -147,6 +147,27 @@ WIRE_SYMBOLS = [
     ("sslsim_decode_grsim_packet", _I, [_VP, C.c_size_t, _I, _VP, _VP, C.POINTER(_I), _VP, C.POINTER(_I),
                                         C.POINTER(C.c_double)]),
 ]
+_LL = C.c_longlong
+MULTI_SYMBOLS = [
+    ("sslsim_shard_range", None, [_LL, _I, _I, C.POINTER(_LL), C.POINTER(_I)]),
+    ("new_world_multi", _VP, [C.POINTER(FieldGeometry), _LL, _I, _VP, _I, _U64, _I, C.POINTER(SimParams)]),
+    ("sslsim_multi_unique_id", _I, [_VP]),
+    ("new_world_multi_rank", _VP, [C.POINTER(FieldGeometry), _LL, _I, _I, _I, _I, _VP, _U64, _I, C.POINTER(SimParams)]),
+    ("delete_world_multi", None, [_VP]), ("world_multi_rank_count", _I, [_VP]), ("world_multi_local_count", _I, [_VP]),
+    ("world_multi_shard", _VP, [_VP, _I]), ("world_multi_shard_rank", _I, [_VP, _I]), ("world_multi_world_count", _LL, [_VP]),
+    ("world_multi_step", _I, [_VP, _I]), ("world_multi_gen_commands", _I, [_VP, _U64, _I]),
+    ("world_multi_set_commands", _I, [_VP, _VP]), ("world_multi_sync", _I, [_VP]),
+    ("world_multi_read_worlds", _I, [_VP, _VP, _I, _VP, _VP, _VP]),
+    ("world_multi_allgather_stats", _I, [_VP, _VP, C.POINTER(BatchStats)]),
+    ("world_multi_timer_start", _I, [_VP]), ("world_multi_timer_stop", _I, [_VP, C.POINTER(_F), _VP]),
+    ("world_multi_error_string", C.c_char_p, [_VP]), ("sslsim_multi_nccl_version", C.c_char_p, []),
+]
+INGEST_SYMBOLS = [
+    ("new_grsim_ingest", _VP, [_VP, _VP, _I, _I, C.c_char_p, C.c_char_p]), ("delete_grsim_ingest", None, [_VP]),
+    ("grsim_ingest_poll", _I, [_VP, _I]), ("grsim_ingest_apply", _I, [_VP]), ("grsim_ingest_port", _I, [_VP, _I]),
+    ("grsim_ingest_packets", C.c_ulonglong, [_VP]), ("grsim_ingest_bad_packets", C.c_ulonglong, [_VP]),
+    ("grsim_ingest_last_timestamp", C.c_double, [_VP, _I]),
+]
 DATA_SYMBOLS = ["FIELD_2014_SINGLE", "FIELD_2014_DOUBLE", "FIELD_2015", "FIELD_DIV_A"]
 
 _LIB = None
@@ -166,7 +187,7 @@ def lib():
             raise RuntimeError("sslsim_b200: %s is missing; build it with __graft_entry__.build() or "
                                "`make -C ssl-sim_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
-        for name, res, args in LEGACY_SYMBOLS + BATCH_SYMBOLS + WIRE_SYMBOLS:
+        for name, res, args in LEGACY_SYMBOLS + BATCH_SYMBOLS + WIRE_SYMBOLS + MULTI_SYMBOLS + INGEST_SYMBOLS:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
@@ -243,6 +264,17 @@ class WorldBatch:
         self.W, self.R, self.N = n_worlds, n_robots, n_robots + 1
         self.seed, self.first_world_id = seed, first_world_id
 
+    @classmethod
+    def from_handle(cls, handle, owner, seed=0x5351, first_world_id=0):
+        """Wrap a `struct WorldBatch *` owned by something else (a WorldMulti shard): close() does not delete it."""
+        L = lib()
+        self = cls.__new__(cls)
+        self._h, self._owner, self._borrowed = handle, owner, True
+        self.W, self.R = L.world_batch_world_count(handle), L.world_batch_robot_count(handle)
+        self.N = self.R + 1
+        self.seed, self.first_world_id = seed, first_world_id
+        return self
+
     def _ck(self, rc):
         if rc < 0:
             raise SslSimError("sslsim_b200 error %d: %s" % (rc, lib().world_batch_error_string(self._h).decode()))
@@ -250,7 +282,8 @@ class WorldBatch:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().delete_world_batch(self._h)
+            if not getattr(self, "_borrowed", False):
+                lib().delete_world_batch(self._h)
             self._h = None
 
     def __del__(self):
@@ -438,6 +471,143 @@ class WorldBatch:
 
     def set_stream(self, cuda_stream):
         self._ck(lib().world_batch_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+
+class GrSimIngest:
+    """include/sslsim_ingest.h: UDP receive -> grSim_Packet decode -> command rows / replacements of the steered worlds."""
+
+    def __init__(self, batch, world_ids, base_port, addr="", iface=""):
+        ids = np.ascontiguousarray(world_ids, np.int32)
+        self._batch = batch
+        self._h = lib().new_grsim_ingest(batch._h, _ptr(ids), ids.size, base_port, addr.encode(), iface.encode())
+        if not self._h:
+            raise SslSimError("new_grsim_ingest failed (bad arguments or socket error)")
+        self.n = ids.size
+
+    def port(self, k):
+        return lib().grsim_ingest_port(self._h, k)
+
+    def poll(self, timeout_ms=0):
+        n = lib().grsim_ingest_poll(self._h, timeout_ms)
+        if n < 0:
+            raise SslSimError("grsim_ingest_poll failed")
+        return n
+
+    def apply(self):
+        return self._batch._ck(lib().grsim_ingest_apply(self._h))
+
+    @property
+    def packets(self):
+        return lib().grsim_ingest_packets(self._h)
+
+    @property
+    def bad_packets(self):
+        return lib().grsim_ingest_bad_packets(self._h)
+
+    def last_timestamp(self, k):
+        return lib().grsim_ingest_last_timestamp(self._h, k)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().delete_grsim_ingest(self._h)
+            self._h = None
+
+
+def _share_torch_nccl():
+    """A Python-process matter, not the library's: PyTorch bundles its own libnccl.so.2 and fails to import if an older
+    one with the same soname is already mapped.  The C library binds NCCL lazily by soname (dlopen), so importing torch
+    first -- when it is installed -- makes both use the one NCCL.  A C/C++ host has no such issue."""
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
+
+
+class WorldMulti:
+    """include/sslsim_multi.h: a batch sharded over several GPUs by contiguous world range, no per-step collective,
+    ncclAllGather of the episode statistics.  devices=[...] = one process driving those GPUs;
+    rank/n_ranks/device/nccl_id = one process per GPU (nccl_id: the 128 bytes of WorldMulti.unique_id() from rank 0)."""
+
+    def __init__(self, total_worlds, n_robots=12, fld="FIELD_2015", devices=None, seed=0x5351, init_mode=0, params=None,
+                 rank=None, n_ranks=None, device=None, nccl_id=None):
+        _share_torch_nccl()
+        L = lib()
+        self._field = field(fld) if isinstance(fld, str) else fld
+        pp = C.byref(params) if params is not None else None
+        if rank is None:
+            devs = np.ascontiguousarray(devices if devices is not None else [0], np.int32)
+            self._h = L.new_world_multi(C.byref(self._field), total_worlds, n_robots, _ptr(devs), devs.size, seed, init_mode, pp)
+        else:
+            buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+            self._h = L.new_world_multi_rank(C.byref(self._field), total_worlds, n_robots, rank, n_ranks, device, buf, seed, init_mode, pp)
+        if not self._h:
+            raise SslSimError("new_world_multi failed (no CUDA device, NCCL missing or bad arguments); no CPU fallback")
+        self.total, self.R, self.N = total_worlds, n_robots, n_robots + 1
+        self.n_ranks, self.n_local = L.world_multi_rank_count(self._h), L.world_multi_local_count(self._h)
+
+    @staticmethod
+    def unique_id():
+        _share_torch_nccl()
+        buf = (C.c_char * 128)()
+        if lib().sslsim_multi_unique_id(buf) < 0:
+            raise SslSimError("ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise SslSimError("sslsim_b200 multi error %d: %s" % (rc, lib().world_multi_error_string(self._h).decode()))
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().delete_world_multi(self._h)
+            self._h = None
+
+    def shard_handle(self, i):
+        return lib().world_multi_shard(self._h, i)
+
+    def shard(self, i=0, seed=0x5351):
+        """local shard i as a WorldBatch (borrowed: every per-batch call works on it)"""
+        L = lib()
+        first, count = C.c_longlong(0), C.c_int(0)
+        L.sslsim_shard_range(self.total, L.world_multi_shard_rank(self._h, i), self.n_ranks, C.byref(first), C.byref(count))
+        return WorldBatch.from_handle(L.world_multi_shard(self._h, i), self, seed=seed, first_world_id=first.value)
+
+    def step(self, n_steps=1):
+        self._ck(lib().world_multi_step(self._h, n_steps))
+
+    def gen_commands(self, period, kind=0):
+        self._ck(lib().world_multi_gen_commands(self._h, period, kind))
+
+    def set_commands(self, cmds):
+        cmds = None if cmds is None else np.ascontiguousarray(cmds, dtype=CMD_DTYPE)
+        self._ck(lib().world_multi_set_commands(self._h, _ptr(cmds)))
+
+    def sync(self):
+        self._ck(lib().world_multi_sync(self._h))
+
+    def read_worlds(self, ids):
+        ids = np.ascontiguousarray(ids, np.int64)
+        pos = np.zeros((ids.size, self.N, 4), np.float32)
+        vel = np.zeros_like(pos)
+        aux = np.zeros((ids.size, 8), np.uint32)
+        n = self._ck(lib().world_multi_read_worlds(self._h, _ptr(ids), ids.size, _ptr(pos), _ptr(vel), _ptr(aux)))
+        return pos, vel, aux, n
+
+    def allgather_stats(self):
+        per = (BatchStats * self.n_ranks)()
+        tot = BatchStats()
+        self._ck(lib().world_multi_allgather_stats(self._h, per, C.byref(tot)))
+        return [p.as_dict() for p in per], tot.as_dict()
+
+    def timer_start(self):
+        self._ck(lib().world_multi_timer_start(self._h))
+
+    def timer_stop(self):
+        mx = C.c_float()
+        per = (C.c_float * self.n_local)()
+        self._ck(lib().world_multi_timer_stop(self._h, C.byref(mx), per))
+        return mx.value, list(per)
 
 
 class World:

@@ -374,7 +374,7 @@ int world_batch_chunk_wait(struct WorldBatch *b, int chunk) {
   return SSLSIM_OK;
 }
 
-static int ensure_cmd_buffer(WorldBatch *b) {
+int sslsim_ensure_cmd_buffer(WorldBatch *b) {
   if (!b->d_cmd && b->R > 0) {
     CK(cudaMalloc(&b->d_cmd, (size_t)b->W * b->R * sizeof(RobotCommand)));
     CK(cudaMemsetAsync(b->d_cmd, 0, (size_t)b->W * b->R * sizeof(RobotCommand), b->stream)); /* passive robots */
@@ -386,7 +386,7 @@ int world_batch_set_commands(struct WorldBatch *b, const struct RobotCommand *ho
   ENTER(b);
   if (!host_cmds) { b->cmd_active = nullptr; return SSLSIM_OK; }
   if (b->R == 0) return SSLSIM_OK;
-  int rc = ensure_cmd_buffer(b);
+  int rc = sslsim_ensure_cmd_buffer(b);
   if (rc) return rc;
   CK(cudaMemcpyAsync(b->d_cmd, host_cmds, (size_t)b->W * b->R * sizeof(RobotCommand), cudaMemcpyHostToDevice,
                      b->stream));
@@ -409,7 +409,7 @@ int world_batch_clear_commands(struct WorldBatch *b) {
 int world_batch_gen_commands(struct WorldBatch *b, uint64_t period, int kind) {
   ENTER(b);
   if (b->R == 0) return SSLSIM_OK;
-  int rc = ensure_cmd_buffer(b);
+  int rc = sslsim_ensure_cmd_buffer(b);
   if (rc) return rc;
   CK(sslsim_launch_gen_commands(b->d_cmd, b->W, b->R, b->seed, b->world0, period, kind, b->stream));
   b->cmd_active = b->d_cmd;

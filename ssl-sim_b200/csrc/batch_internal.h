@@ -74,6 +74,7 @@ struct World {
 
 bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what);
 int sslsim_join_chunks(WorldBatch *b); /* orders the batch stream after everything queued on the chunk streams */
+extern "C" int sslsim_ensure_cmd_buffer(WorldBatch *b); /* the batch-owned command buffer, zeroed (= passive robots) on first use */
 WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_robots, int cap_bodies, int device,
                                 uint64_t seed, uint64_t world0, int init_mode, const SslSimParams *params,
                                 bool run_init);

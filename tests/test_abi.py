@@ -33,11 +33,12 @@ def _declared_functions(path):
 def test_every_declared_symbol_is_exported(sim):
     L = sim.lib()
     declared = (_declared_functions(os.path.join(INC, "sslsim.h")) + _declared_functions(os.path.join(INC, "sslsim_batch.h")) +
-                _declared_functions(os.path.join(INC, "serialize.h")))
-    assert len(declared) >= 37 + 30 + 5
+                _declared_functions(os.path.join(INC, "serialize.h")) + _declared_functions(os.path.join(INC, "sslsim_multi.h")) +
+                _declared_functions(os.path.join(INC, "sslsim_ingest.h")))
+    assert len(declared) >= 37 + 30 + 5 + 15
     missing = [n for n in declared if not hasattr(L, n)]
     assert not missing, missing
-    bound = {n for n, _, _ in sim.LEGACY_SYMBOLS + sim.BATCH_SYMBOLS + sim.WIRE_SYMBOLS}
+    bound = {n for n, _, _ in sim.LEGACY_SYMBOLS + sim.BATCH_SYMBOLS + sim.WIRE_SYMBOLS + sim.MULTI_SYMBOLS + sim.INGEST_SYMBOLS}
     assert set(declared) <= bound, set(declared) - bound      # the Python mirror binds all of them
     for d in sim.DATA_SYMBOLS:
         sim.FieldGeometry.in_dll(L, d)
@@ -131,4 +132,7 @@ def test_product_does_not_touch_oracle():
                 if fn.endswith((".py", ".cu", ".h", ".cpp", ".c", "Makefile")):
                     txt = open(os.path.join(dp, fn), errors="ignore").read()
                     assert not re.search(r'#include\s*[<"][^>"]*oracle|import\s+oracle|from\s+oracle|\borc_\w+\s*\(|'
-                                         r'libssl_oracle|dlopen', txt), (dp, fn)
+                                         r'libssl_oracle|warp_emu|step_kernel_emu', txt.replace("tests/warp_emu", "")), (dp, fn)
+                    # the only run-time loading the product does is NCCL (sslsim_multi.h): every dlopen names libnccl
+                    for call in re.findall(r'dlopen\s*\(([^;]*);', txt):
+                        assert fn == "multi.cu" and '"libnccl' in call, (dp, fn, call)
