@@ -413,26 +413,6 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   uint32_t cflags[ORC_MAX_BODIES];
   for (int b = 0; b < N; b++) { ex[b] = ey[b] = ez[b] = ew[b] = 0.0f; cflags[b] = 0; }
 
-  /* 4.0 simulation islands (Bullet btSimulationIslandManager::buildIslands, restated for a scene whose only
-   * body that may sleep is the ball): the ball shares an island with a robot iff their broadphase boxes overlap
-   * -- closed form [DEV]: horizontal distance of the ball centre from the robot axis <= ROBOT_REACH + BALL_R +
-   * 2 margins (each shape grown by the contact breaking threshold).  An island with a robot never sleeps and
-   * wakes a sleeping ball (ISLAND_SLEEPING -> WANTS_DEACTIVATION, time 0); a ball alone sleeps as soon as it
-   * wants to. */
-  uint32_t act = (aux[ORC_AUX_STATUS] >> ACT_SHIFT) & 3u, cnt = aux[ORC_AUX_STATUS] >> CNT_SHIFT;
-  if (act != ACT_ACTIVE) {
-    int near = 0;
-    const float lim = ROBOT_REACH + BALL_R + 2.0f * MARGIN;
-    for (int r = 0; r < R; r++) {
-      float dx = pos[B].x - pos[r].x, dy = pos[B].y - pos[r].y;
-      float d2 = dot2(dx, dy, dx, dy);
-      near |= d2 <= lim * lim;
-    }
-    if (near) { if (act == ACT_ASLEEP) { act = ACT_WANTS; cnt = 0; } }
-    else act = ACT_ASLEEP;
-  }
-  const int asleep = act == ACT_ASLEEP; /* not solved, not integrated (btRigidBody::isActive() is false) */
-
   /* 4.1 actuation (new functionality; command schema reference protos/grSim_Commands.proto) */
   if (cmd) {
     int kicker = -1, dribbler = -1;
@@ -494,7 +474,6 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
         ew[r] = (WHEEL_RC * tq) * (h / p->robot_yaw_inertia);
       }
     }
-    /* (the capture boxes lie inside the island box of 4.0, so a kicked or dribbled ball is never asleep) */
     if (kicker >= 0) {
       vel[B].x = kvx; vel[B].y = kvy; vel[B].z = kvz;
       float s2 = dot3(kvx, kvy, kvz, kvx, kvy, kvz);
@@ -503,12 +482,13 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
       aux[ORC_AUX_OUTS] += 1u << 16;
     }
     if (dribbler >= 0 && kicker < 0) { ex[B] = dax * h; ey[B] = day * h; }
+    /* a kicker or dribbler acting on the ball wakes it, like btRigidBody::activate() */
+    if (kicker >= 0 || dribbler >= 0) aux[ORC_AUX_STATUS] &= (1u << ACT_SHIFT) - 1u;
   }
   /* 4.2 gravity as an external impulse (Bullet: totalForce * invMass * h).  applyGravity runs once per
    * stepSimulation and skips a body that is asleep at that moment: ball_gravity is latched by orc_step. */
   const float gh = GRAV * h;
   for (int b = 0; b < N; b++) if (b != B || ball_gravity) ez[b] = ez[b] - gh;
-  if (asleep) { ex[B] = 0.0f; ey[B] = 0.0f; ez[B] = 0.0f; }
 
   /* solver velocities start at v + external impulse */
   float vx[ORC_MAX_BODIES], vy[ORC_MAX_BODIES], vz[ORC_MAX_BODIES];
@@ -520,16 +500,45 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
     invm[b] = b == B ? 1.0f / BALL_M : 1.0f / ROBOT_M;
   }
 
+  /* the ball's contact margin: Bullet's breaking threshold + the distance it may travel this substep, which stands
+   * in for Bullet's predictive (CCD) contact on the ball (reference :58-59) */
+  float ball_margin;
+  {
+    float s2 = dot3(vx[B], vy[B], vz[B], vx[B], vy[B], vz[B]);
+    ball_margin = mad(h, sqrtf(s2), MARGIN);
+  }
+
+  /* 4.0 simulation islands (Bullet btSimulationIslandManager::buildIslands, restated for a scene whose only
+   * body that may sleep is the ball): the ball shares an island with a robot iff their broadphase boxes overlap
+   * -- closed form [DEV]: the ball-robot pair passes the pair broadphase, i.e. the horizontal distance of the ball
+   * centre from the robot axis is <= ROBOT_R + BALL_R + ball margin (the distance inside which a contact row can
+   * exist at all).  An island with a robot never sleeps and wakes a sleeping ball (ISLAND_SLEEPING ->
+   * WANTS_DEACTIVATION, time 0); a ball alone sleeps as soon as it wants to. */
+  uint32_t act = (aux[ORC_AUX_STATUS] >> ACT_SHIFT) & 3u, cnt = aux[ORC_AUX_STATUS] >> CNT_SHIFT;
+  if (act != ACT_ACTIVE) {
+    int near = 0;
+    const float lim = ROBOT_R + BALL_R + ball_margin;
+    for (int r = 0; r < R; r++) {
+      float dx = pos[B].x - pos[r].x, dy = pos[B].y - pos[r].y;
+      float d2 = dot2(dx, dy, dx, dy);
+      near |= d2 <= lim * lim;
+    }
+    if (near) { if (act == ACT_ASLEEP) { act = ACT_WANTS; cnt = 0; } }
+    else act = ACT_ASLEEP;
+  }
+  const int asleep = act == ACT_ASLEEP; /* not solved, not integrated (btRigidBody::isActive() is false) */
+  if (asleep) { /* no external impulse on a sleeping body; no predictive contact either */
+    vx[B] = vel[B].x; vy[B] = vel[B].y; vz[B] = vel[B].z;
+    ball_margin = MARGIN;
+  }
+
   /* 4.3 contact generation on substep-start positions */
   gen_ctx g;
   g.n = N; g.R = R; g.h = h; g.inv_h = inv_h; g.pos = pos; g.vel = vel; g.spin_mode = spin_mode;
   g.cflags = cmd ? cflags : 0;
   g.hvx = vx; g.hvy = vy; g.hvz = vz;
   g.rest_thresh = p->restitution_threshold;
-  {
-    float s2 = dot3(vx[B], vy[B], vz[B], vx[B], vy[B], vz[B]);
-    g.ball_margin = asleep ? MARGIN : mad(h, sqrtf(s2), MARGIN); /* stands in for Bullet's predictive (CCD) contact */
-  }
+  g.ball_margin = ball_margin;
   row_t rows[MAX_SERIAL_ROWS];
   row_t ground[ORC_MAX_BODIES];
   int has_ground[ORC_MAX_BODIES];

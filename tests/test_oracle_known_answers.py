@@ -243,9 +243,13 @@ def test_moving_ball_does_not_sleep_and_robot_wakes_it(orc):
     assert _act(w) == (0, 0)
     w.step(600)
     assert _act(w)[0] == 2                       # stopped, then slept
-    # a robot whose shapes come within the broadphase margins of the ball wakes it: asleep -> wants, time 0
+    # a robot that comes within contact reach of the ball (the pair passes the broadphase: axis distance <= 0.09 +
+    # 0.0215 + margin 0.02) wakes it: asleep -> wants, time 0; one that stays just outside does not
     bx = float(w.pos[0, 1, 0])
-    w.pos[0, 0, :2] = (bx + 0.15, 0.0)
+    w.pos[0, 0, :2] = (bx + 0.14, 0.0)
+    w.step(1, substeps=1)
+    assert _act(w)[0] == 2
+    w.pos[0, 0, :2] = (bx + 0.13, 0.0)
     w.step(1, substeps=1)
     assert _act(w) == (1, 1) and float(w.vel[0, 1, 2]) == 0.0   # awake, but gravity was not applied this step
     w.step(1)
