@@ -26,7 +26,7 @@ for rep in 1 2; do for v in ${names[@]}; do
 done; done
 if [ -n "$NCU" ]; then for v in ${names[@]}; do
   cp tools/_lib_\$v.so ssl-sim_b200/libsslsim_b200.so
-  ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,smsp__cycles_active.avg,sm__cycles_elapsed.max,smsp__issue_active.avg --clock-control none -k regex:step_worlds -s 45 -c 1 --csv python tools/var_time.py \$v 131072 2>/dev/null | grep -E "step_worlds" | awk -F'","' -v v=\$v '{print "ncu", v, \$(NF-2), \$NF}'
+  ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,smsp__cycles_active.avg,sm__cycles_elapsed.max,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__icc_request_hit_rate.pct --clock-control none -k regex:step_worlds -s 41 -c 1 --csv python tools/var_time.py \$v 131072 2>/dev/null | grep "step_worlds" | awk -F'","' -v v=\$v '{gsub(/"/,"",\$NF); print "ncu", v, \$(NF-2), \$NF}'
 done; fi
 cp /tmp/orig.so ssl-sim_b200/libsslsim_b200.so
 EOS
