@@ -1,5 +1,5 @@
 """Turn gpurun_out/{launches.csv, prof_*.ncu-rep, bench_*.json} into the tracked summaries under profiles/.
-usage: python tools/make_profile_summary.py <tag> [ncu-rep] [launches.csv] [bench.json] [world-steps per launch]"""
+usage: python tools/make_profile_summary.py <tag> [ncu-rep] [launches.csv] [bench.json] [world-steps per launch] [worlds] [command]"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
@@ -7,6 +7,8 @@ rep = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out/prof_
 launches = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out/launches.csv")
 bench = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "gpurun_out/bench_r1.json")
 WSPL = int(sys.argv[5]) if len(sys.argv) > 5 else 4096 * 30 * 10   # worlds x world-steps of one captured launch
+WORLDS = int(sys.argv[6]) if len(sys.argv) > 6 else 4096
+CMD = sys.argv[7] if len(sys.argv) > 7 else "python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --large-worlds 0"
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 
@@ -23,9 +25,8 @@ for r in rows[h + 1:]:
             pass
 tot = sum(sum(v) for v in agg.values())
 with open(os.path.join(out, tag + "_launches.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 300: python bench.py --steps 20 --warmup 3 "
-            "--no-cpu-baseline --no-e2e --large-worlds 0 (4096 6v6 worlds; warm-up and the per-period pass launch 30 "
-            "world-steps, the fused pass %d world-steps per step_worlds launch)\n" % (WSPL // 4096))
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none: %s (%d 6v6 worlds; the fused pass runs %d "
+            "world-steps per step_worlds launch)\n" % (CMD, WORLDS, WSPL // WORLDS))
     f.write("per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes\n\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write("%-70s launches %3d  total %9.1f us  avg %8.1f us  share %5.1f%%\n" %
@@ -45,7 +46,7 @@ keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__inst_executed_pipe_fma.sum",
         "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_xu.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 with open(os.path.join(out, tag + "_step_worlds_ncu.txt"), "w") as f:
-    f.write("ncu --set full --clock-control none --import-source on -k regex:step_worlds -s 5 -c 3: same command\n")
+    f.write("ncu --set full --clock-control none --import-source on -k regex:step_worlds: %s\n" % CMD)
     for i, hname in enumerate(hdr):
         if hname in keep or ("issue_stalled" in hname and hname.endswith("per_issue_active.ratio")):
             f.write("%-82s %-16s %s\n" % (hname, units[i], " | ".join(r[i] for r in data)))
@@ -57,8 +58,8 @@ tr = sum(tobytes(r[ir], units[ir]) + tobytes(r[iw], units[iw]) for r in data) / 
 ii = hdr.index("smsp__inst_executed.sum")
 inst = sum(float(r[ii].replace(",", "")) for r in data) / len(data)
 json.dump({"dram_bytes_per_launch": tr, "warp_instructions_per_launch": inst,
-           "world_steps_per_launch": WSPL, "launch_shape": "4096 6v6 worlds x %d world-steps" % (WSPL // 4096),
-           "kernel": "step_worlds", "source": os.path.basename(rep),
+           "world_steps_per_launch": WSPL, "launch_shape": "%d 6v6 worlds x %d world-steps" % (WORLDS, WSPL // WORLDS),
+           "kernel": "step_worlds", "source": os.path.basename(rep), "capture": tag,
            "how": "dram__bytes_read.sum + dram__bytes_write.sum, mean over %d captured launches, ncu --set full" % len(data)},
           open(os.path.join(out, "traffic.json"), "w"), indent=1)
 
