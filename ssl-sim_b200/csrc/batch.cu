@@ -153,6 +153,7 @@ static StepArgs step_args(const WorldBatch *b, int first, int count, const Robot
 int sslsim_batch_step(WorldBatch *b, int n_steps, int substeps, float h, float time_step_total, int steps_per_period,
                       long long cmd_period_stride) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_step");
   if (n_steps < 0 || substeps < 0) return SSLSIM_E_ARG;
   if (n_steps > 0 && substeps >= 0) {
     const StepArgs a = step_args(b, 0, b->W, b->cmd_active, n_steps, substeps, h, steps_per_period, cmd_period_stride);
@@ -214,6 +215,7 @@ void delete_world_batch(struct WorldBatch *batch) { batch_free(batch); }
 
 int world_batch_reset(struct WorldBatch *b, uint64_t seed, int init_mode) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_reset");
   b->seed = seed;
   CK(sslsim_launch_init(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->field, seed, b->world0, init_mode, b->stream));
   b->frame = 0; b->timestamp = 0.0f;
@@ -239,6 +241,7 @@ int world_batch_step_delta(struct WorldBatch *b, int n_steps, int substeps, floa
 int world_batch_step_sequence(struct WorldBatch *b, const struct RobotCommand *dev_cmds, int n_periods,
                               int steps_per_period) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_step_sequence");
   if (!dev_cmds || n_periods <= 0 || steps_per_period <= 0) return SSLSIM_E_ARG;
   const long long stride = (long long)b->W * b->R;
   b->cmd_active = dev_cmds;
@@ -251,6 +254,7 @@ int world_batch_step_sequence(struct WorldBatch *b, const struct RobotCommand *d
 int world_batch_step_sequence_host(struct WorldBatch *b, const struct RobotCommand *host_cmds, int n_periods,
                                    int steps_per_period) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_step_sequence_host");
   if (!host_cmds || n_periods <= 0 || steps_per_period <= 0) return SSLSIM_E_ARG;
   const size_t n = (size_t)n_periods * b->W * b->R;
   if (n > b->seq_cap) {
@@ -265,6 +269,7 @@ int world_batch_step_sequence_host(struct WorldBatch *b, const struct RobotComma
 
 int world_batch_sync(struct WorldBatch *b) {
   ENTER(b); /* joins the chunk streams first */
+  SSLSIM_RANGE("world_batch_sync");
   CK(cudaStreamSynchronize(b->stream));
   return SSLSIM_OK;
 }
@@ -305,6 +310,7 @@ int world_batch_chunk_range(const struct WorldBatch *b, int chunk, int *first_wo
 int world_batch_chunk_step(struct WorldBatch *b, int chunk, const struct RobotCommand *host_cmds, int n_steps,
                            uint32_t *host_aux) {
   ENTER_NOJOIN(b);
+  SSLSIM_RANGE("world_batch_chunk_step");
   if (chunk < 0 || chunk >= (int)b->chunks.size() || n_steps < 0) return SSLSIM_E_ARG;
   WorldBatch::Chunk &k = b->chunks[chunk];
   /* after whatever was queued on the batch stream before this call */
@@ -350,6 +356,7 @@ int world_batch_chunk_step_ex(struct WorldBatch *b, int chunk, const struct Robo
 int world_batch_chunk_step_sequence(struct WorldBatch *b, int chunk, const struct RobotCommand *dev_cmds, int n_periods,
                                     int steps_per_period) {
   ENTER_NOJOIN(b);
+  SSLSIM_RANGE("world_batch_chunk_step_sequence");
   if (chunk < 0 || chunk >= (int)b->chunks.size() || !dev_cmds || n_periods <= 0 || steps_per_period <= 0)
     return SSLSIM_E_ARG;
   WorldBatch::Chunk &k = b->chunks[chunk];
@@ -369,6 +376,7 @@ int world_batch_chunk_step_sequence(struct WorldBatch *b, int chunk, const struc
 
 int world_batch_chunk_wait(struct WorldBatch *b, int chunk) {
   ENTER_NOJOIN(b);
+  SSLSIM_RANGE("world_batch_chunk_wait");
   if (chunk < 0 || chunk >= (int)b->chunks.size()) return SSLSIM_E_ARG;
   CK(cudaStreamSynchronize(b->chunks[chunk].stream));
   return SSLSIM_OK;
@@ -384,6 +392,7 @@ int sslsim_ensure_cmd_buffer(WorldBatch *b) {
 
 int world_batch_set_commands(struct WorldBatch *b, const struct RobotCommand *host_cmds) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_set_commands");
   if (!host_cmds) { b->cmd_active = nullptr; return SSLSIM_OK; }
   if (b->R == 0) return SSLSIM_OK;
   int rc = sslsim_ensure_cmd_buffer(b);
@@ -408,6 +417,7 @@ int world_batch_clear_commands(struct WorldBatch *b) {
 
 int world_batch_gen_commands(struct WorldBatch *b, uint64_t period, int kind) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_gen_commands");
   if (b->R == 0) return SSLSIM_OK;
   int rc = sslsim_ensure_cmd_buffer(b);
   if (rc) return rc;
@@ -418,6 +428,7 @@ int world_batch_gen_commands(struct WorldBatch *b, uint64_t period, int kind) {
 
 int world_batch_gen_commands_into(struct WorldBatch *b, struct RobotCommand *dev_out, uint64_t period, int kind) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_gen_commands_into");
   if (!dev_out) return SSLSIM_E_ARG;
   CK(sslsim_launch_gen_commands(dev_out, b->W, b->R, b->seed, b->world0, period, kind, b->stream));
   return SSLSIM_OK;
@@ -436,6 +447,7 @@ static int ensure_rep(WorldBatch *b, size_t bytes) {
 
 int world_batch_replace_robots(struct WorldBatch *b, const struct RobotReplacement *recs, int n) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_replace_robots");
   if (n < 0 || (n > 0 && !recs)) return SSLSIM_E_ARG;
   if (n == 0) return SSLSIM_OK;
   int rc = ensure_rep(b, (size_t)n * sizeof(RobotReplacement));
@@ -449,6 +461,7 @@ int world_batch_replace_robots(struct WorldBatch *b, const struct RobotReplaceme
 
 int world_batch_replace_balls(struct WorldBatch *b, const struct BallReplacement *recs, int n) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_replace_balls");
   if (n < 0 || (n > 0 && !recs)) return SSLSIM_E_ARG;
   if (n == 0) return SSLSIM_OK;
   int rc = ensure_rep(b, (size_t)n * sizeof(BallReplacement));
@@ -462,6 +475,7 @@ int world_batch_replace_balls(struct WorldBatch *b, const struct BallReplacement
 
 int world_batch_read_state(struct WorldBatch *b, float *pos, float *vel, uint32_t *aux) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_read_state");
   const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4);
   if (pos) CK(cudaMemcpyAsync(pos, b->d_pos, nb, cudaMemcpyDeviceToHost, b->stream));
   if (vel) CK(cudaMemcpyAsync(vel, b->d_vel, nb, cudaMemcpyDeviceToHost, b->stream));
@@ -473,6 +487,7 @@ int world_batch_read_state(struct WorldBatch *b, float *pos, float *vel, uint32_
 /* bulk readout of selected worlds: pos/vel [n][n_robots + 1][4], aux [n][8]; any pointer may be NULL */
 int world_batch_read_worlds(struct WorldBatch *b, const int *world_ids, int n, float *pos, float *vel, uint32_t *aux) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_read_worlds");
   if (n < 0 || (n > 0 && !world_ids)) return SSLSIM_E_ARG;
   const size_t N = (size_t)b->R + 1;
   for (int i = 0; i < n; ++i) {
@@ -490,6 +505,7 @@ int world_batch_read_aux(struct WorldBatch *b, uint32_t *aux) { return world_bat
 
 int world_batch_write_state(struct WorldBatch *b, const float *pos, const float *vel, const uint32_t *aux) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_write_state");
   const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4);
   if (pos) CK(cudaMemcpyAsync(b->d_pos, pos, nb, cudaMemcpyHostToDevice, b->stream));
   if (vel) CK(cudaMemcpyAsync(b->d_vel, vel, nb, cudaMemcpyHostToDevice, b->stream));
@@ -514,6 +530,7 @@ size_t world_batch_detection_record_size(const struct WorldBatch *b) {
 
 int world_batch_gather_detections(struct WorldBatch *b, const int *world_ids, int n, void *out, size_t capacity) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_gather_detections");
   if (n < 0 || (n > 0 && (!world_ids || !out))) return SSLSIM_E_ARG;
   const size_t rec = world_batch_detection_record_size(b);
   if ((size_t)n * rec > capacity) return SSLSIM_E_SPACE;
@@ -539,6 +556,7 @@ int world_batch_gather_detections(struct WorldBatch *b, const int *world_ids, in
 
 int world_batch_referee(struct WorldBatch *b) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_referee");
   CK(sslsim_launch_referee(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->field.field_length, b->field.field_width, b->stream));
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;
@@ -573,6 +591,7 @@ struct WorldSnapshot *world_batch_snapshot(struct WorldBatch *b) {
 
 int world_batch_restore(struct WorldBatch *b, const struct WorldSnapshot *s) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_restore");
   if (!s || s->W != b->W || s->R != b->R || s->device != b->device) return SSLSIM_E_ARG;
   const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4), na = (size_t)b->W * 8 * sizeof(uint32_t);
   CK(cudaMemcpyAsync(b->d_pos, s->pos, nb, cudaMemcpyDeviceToDevice, b->stream));
@@ -592,6 +611,7 @@ void world_snapshot_free(struct WorldSnapshot *s) {
 
 int world_batch_fork(struct WorldBatch *b, int src, const int *dst, int n) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_fork");
   if (src < 0 || src >= b->W || n < 0 || (n > 0 && !dst)) return SSLSIM_E_ARG;
   if (n == 0) return SSLSIM_OK;
   int rc = ensure_rep(b, (size_t)n * sizeof(int));
@@ -605,6 +625,7 @@ int world_batch_fork(struct WorldBatch *b, int src, const int *dst, int n) {
 
 int world_batch_reduce_stats(struct WorldBatch *b, struct BatchStats *out) {
   ENTER(b);
+  SSLSIM_RANGE("world_batch_reduce_stats");
   if (!out) return SSLSIM_E_ARG;
   CK(sslsim_launch_reduce(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->world0, b->d_stats, b->stream));
   unsigned long long h[8];

@@ -6,6 +6,22 @@
 #include <vector>
 #include "dev_types.h"
 
+/* NVTX ranges around every launch site of the C ABI (tracing hooks), so a timeline (nsys, ncu --nvtx) shows
+ * which API call a kernel or copy belongs to.  Header-only NVTX v3: without a tool attached a range is one
+ * predictable branch.  -DSSLSIM_NO_NVTX compiles them out. */
+#ifndef SSLSIM_NO_NVTX
+#include <nvtx3/nvToolsExt.h>
+struct SslsimRange {
+  explicit SslsimRange(const char *name) { nvtxRangePushA(name); }
+  ~SslsimRange() { nvtxRangePop(); }
+  SslsimRange(const SslsimRange &) = delete;
+  SslsimRange &operator=(const SslsimRange &) = delete;
+};
+#define SSLSIM_RANGE(name) SslsimRange sslsim_range_(name)
+#else
+#define SSLSIM_RANGE(name) do { } while (0)
+#endif
+
 #define SSLSIM_LEGACY_MAX_ROBOTS 100 /* reference src/sslsim.cpp:215 stack_vector<Robot,100> */
 #define SSLSIM_LEGACY_MAX_BALLS 20   /* reference src/sslsim.cpp:214 */
 #define SSLSIM_MAX_BODIES 32

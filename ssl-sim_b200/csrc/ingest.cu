@@ -78,6 +78,7 @@ struct GrSimIngest *new_grsim_ingest(struct WorldBatch *b, const int *world_ids,
 }
 
 int grsim_ingest_poll(struct GrSimIngest *g, int timeout_ms) {
+  SSLSIM_RANGE("grsim_ingest_poll");
   if (!g) return SSLSIM_E_ARG;
   const int n = (int)g->fds.size(), R = g->b->R;
   std::vector<pollfd> pf(n);
@@ -108,6 +109,7 @@ int grsim_ingest_poll(struct GrSimIngest *g, int timeout_ms) {
 }
 
 int grsim_ingest_apply(struct GrSimIngest *g) {
+  SSLSIM_RANGE("grsim_ingest_apply");
   if (!g) return SSLSIM_E_ARG;
   WorldBatch *b = g->b;
   int rc = world_batch_sync(b); /* joins chunk streams; the steps queued so far read the old rows */

@@ -214,6 +214,7 @@ int world_multi_read_worlds(struct WorldMulti *m, const long long *ids, int n, f
 }
 
 int world_multi_allgather_stats(struct WorldMulti *m, struct BatchStats *per_shard, struct BatchStats *total) {
+  SSLSIM_RANGE("world_multi_allgather_stats");
   if (!m) return SSLSIM_E_ARG;
   if (m->comms.size() != m->shards.size()) return fail(m, SSLSIM_E_NCCL, "world_multi_allgather_stats", "no communicator");
   /* K4 on every local shard, on its own stream */
