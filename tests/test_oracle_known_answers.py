@@ -283,3 +283,26 @@ def test_readout_yaw_follows_bullets_quaternion_readout(orc):
         assert float(orc.readout_yaw(yaw)) == pytest.approx(want, abs=1e-6), yaw
     z = orc.readout_yaw(0.0)
     assert z == 0.0 and np.signbit(z)
+
+
+def test_declared_deviation_d4_contacts_use_the_chassis_radius_only(orc):
+    """STEP_SPEC section 9, D4 (declared deviation, pinned here so that it cannot change unnoticed): the reference's robot
+    is a compound of the chassis cylinder (r = 0.09) and four wheel discs reaching to 0.10 (src/sslsim.cpp:81-98); the
+    spec's wall, robot-robot and ball-robot contacts use the chassis cylinder alone.  A robot driven into the +x wall
+    with a wheel (mounted at 60 degrees from its heading) pointing straight at the wall is turned back with its axis
+    0.09 m from the wall, where Bullet's compound shape would stop it at 0.10 m; two robots pushed together get as close as
+    0.18 m axis to axis whatever their headings."""
+    w = _one_world(orc, R=3)
+    yaw = np.float32(np.deg2rad(60.0))                         # wheel 0 (60 degrees about -z) points along +x
+    w.pos[0, 0] = (5.05, 0.0, 0.025, yaw); w.vel[0, 0, 0] = 0.6
+    w.pos[0, 1] = (0.0, 1.0, 0.025, 0.0); w.vel[0, 1, 0] = 1.0  # robot 1 runs into robot 2
+    w.pos[0, 2] = (0.3, 1.0, 0.025, yaw)
+    w.pos[0, 3] = (0.0, -2.0, 0.0215, 0.0)
+    min_gap, max_x = 1.0, 0.0
+    for _ in range(240):
+        w.step(1)
+        min_gap = min(min_gap, float(w.pos[0, 2, 0] - w.pos[0, 1, 0]))
+        max_x = max(max_x, float(w.pos[0, 0, 0]))
+    wall = 9.0 / 2 + 0.25 + 0.45                                # FIELD_2015: field_length / 2 + boundary + referee = 5.2
+    assert wall - 0.09 - 4e-3 < max_x < wall - 0.09 + 1e-3      # turned back at the chassis radius (within a substep's travel), not at the 0.10 wheel reach
+    assert 0.18 - 3e-3 < min_gap < 0.18 + 8e-3                  # chassis to chassis (0.20 with both wheels in line)

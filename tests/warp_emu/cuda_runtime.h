@@ -58,7 +58,7 @@ int lane_id();
 #define blockDim (emu::t_blockDim)
 #define gridDim (emu::t_gridDim)
 
-enum { EMU_TAG_SYNC = 1, EMU_TAG_SHFL, EMU_TAG_SHFL_UP, EMU_TAG_BALLOT, EMU_TAG_ANY, EMU_TAG_RED_OR, EMU_TAG_RED_MAX };
+enum { EMU_TAG_SYNC = 1, EMU_TAG_SHFL, EMU_TAG_SHFL_UP, EMU_TAG_BALLOT, EMU_TAG_ANY, EMU_TAG_RED_OR, EMU_TAG_RED_MAX, EMU_TAG_RED_ADD };
 
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
@@ -108,6 +108,13 @@ static inline int __reduce_max_sync(unsigned, int v) {
   emu::gather(EMU_TAG_RED_MAX, emu_pack(v), all);
   int r = emu_unpack<int>(all[0]);
   for (int i = 1; i < 32; ++i) { const int t = emu_unpack<int>(all[i]); r = t > r ? t : r; }
+  return r;
+}
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+  uint64_t all[32];
+  emu::gather(EMU_TAG_RED_ADD, v, all);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r += (unsigned)all[i];
   return r;
 }
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p += v; return o; }

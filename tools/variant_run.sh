@@ -30,5 +30,10 @@ if [ -n "$NCU" ]; then for v in ${names[@]}; do
 done; fi
 cp /tmp/orig.so ssl-sim_b200/libsslsim_b200.so
 EOS
-/usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/_var_run.sh' 2>&1 | grep -vE "^\[gpurun\] sending"
+for try in 1 2 3 4 5 6 7 8; do   # the pod sometimes answers "transient" (nothing charged): retry
+  /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/_var_run.sh' > /tmp/_gpurun_variant.log 2>&1
+  grep -q "status=transient" /tmp/_gpurun_variant.log || break
+  sleep 120
+done
+grep -vE "^\[gpurun\] sending" /tmp/_gpurun_variant.log
 for n in "${names[@]}"; do rm -f "tools/_lib_$n.so"; done; rm -f tools/_var_run.sh
