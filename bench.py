@@ -379,6 +379,10 @@ def main():
         e2e = {"value": units / e_s, "unit": "world-steps/s",
                "h2d_bytes_per_step": PPS * cmd_bytes * world_size, "d2h_bytes_per_step": PPS * W * 32 * world_size,
                "ms_per_step": e_s * 1e3 / K, "chunks": nch, "api": api % (nch, PERIOD_STEPS, ""),
+               "commands": "%d host command sets (generator periods 100000..) used in turn -- a full step's worth of distinct "
+                           "host blocks would need %.0f GB of pinned memory -- so the e2e worlds follow a different command "
+                           "stream than the device arm's (fresh draws every period) and cost a few percent less per step; the "
+                           "two arms are checked against the oracle separately (parity)" % (N_HOST, K * PPS * cmd_bytes / 1e9),
                "with_state": {"value": units / s_s, "unit": "world-steps/s", "ms_per_step": s_s * 1e3 / K,
                               "h2d_bytes_per_step": PPS * cmd_bytes * world_size,
                               "d2h_bytes_per_step": PPS * W * (32 + 2 * NB) * world_size,

@@ -791,3 +791,84 @@ def test_other_fields_and_iteration_counts(sim, orc, fld, iters):
         b.gen_commands(period, 1)
         b.step(30); o.step(30)
     _compare(b.read_state(), o, 240, "%s iters=%d" % (fld, iters))
+
+
+def _compare_sampled(b, o, ids, tag):
+    """sampled worlds of a large batch (global ids `ids`) against the oracle worlds built with the same ids"""
+    pos, vel, aux = b.read_worlds(ids)
+    ok = ((o.aux[:, 0] >> 16) & 1) == 0          # overflowed worlds: state unspecified (STEP_SPEC 4.3)
+    np.testing.assert_array_equal((aux[:, 0] >> 16) & 1, (o.aux[:, 0] >> 16) & 1, err_msg=tag)
+    np.testing.assert_array_equal(aux[:, 7], o.aux[:, 7], err_msg=tag)
+    np.testing.assert_array_equal(pos[ok], o.pos[ok], err_msg="pos " + tag)
+    np.testing.assert_array_equal(vel[ok], o.vel[ok], err_msg="vel " + tag)
+    np.testing.assert_array_equal(aux[ok], o.aux[ok], err_msg="aux " + tag)
+    return int(ok.sum())
+
+
+def test_config2_full_size_sampled_worlds(sim, orc):
+    """BASELINE configs[1] at its stated size: 4,096 6v6 worlds, 600-step episode, wheel commands redrawn every 30
+    steps; the 64 worlds with id = 0 mod 64 bit-identical to the oracle after every period."""
+    W, R = 4096, 12
+    ids = list(range(0, W, 64))
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(len(ids), R, world_ids=ids)
+    T = os.cpu_count() or 1
+    for period in range(20):
+        b.gen_commands(period, 0); o.gen_commands(period, 0)
+        b.step(30); o.step(30, threads=T)
+        assert _compare_sampled(b, o, ids, "period %d" % period) == len(ids)
+    assert b.reduce_stats()["bad_worlds"] == 0
+
+
+def test_config3_full_size_sampled_worlds(sim, orc):
+    """BASELINE configs[2] at its stated size: 65,536 crowded 11v11 worlds on the Division-A field, kicks and
+    dribbling, 300 steps; 32 sampled worlds (ids k * 2048) bit-identical to the oracle."""
+    W, R = 65536, 22
+    ids = list(range(0, W, 2048))
+    b = sim.WorldBatch(W, R, fld="FIELD_DIV_A", init_mode=1)
+    o = orc.Worlds(len(ids), R, fld=orc.FIELD_DIV_A, mode=1, world_ids=ids)
+    T = os.cpu_count() or 1
+    for period in range(10):
+        b.gen_commands(period, 1); o.gen_commands(period, 1)
+        b.step(30); o.step(30, threads=T)
+    n = _compare_sampled(b, o, ids, "after 300 steps")
+    assert n >= len(ids) - 4           # (a crowded world may overflow its 64 rows; the flag itself is compared above)
+    assert int(o.aux[:, 7].astype(np.uint64).sum()) > 300 * 2 * 23 * len(ids)
+
+
+def test_config4_full_size_sampled_worlds_and_gather(sim, orc):
+    """BASELINE configs[3] at its stated size: 16,384 6v6 worlds, spinner + kicks every step, detection records of 64
+    observed worlds (ids k * 256) gathered after every world-step; the observed worlds and every gathered record
+    bit-identical to the oracle."""
+    W, R = 16384, 12
+    ids = list(range(0, W, 256))
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(len(ids), R, world_ids=ids)
+    T = os.cpu_count() or 1
+    b.gen_commands(0, 0); o.gen_commands(0, 0)
+    b.step(120); o.step(120, threads=T)                # drop and settle
+    robot_ids = np.arange(R) // 2                      # roster B0,Y0,B1,... (src/main.c:65-68): id = slot / 2
+    for step in range(150):
+        b.gen_commands(1 + step, 1); o.gen_commands(1 + step, 1)
+        b.step(1); o.step(1, threads=T)
+        if step % 10 == 9:
+            rec = b.gather_detections(ids)
+            for k in (0, 17, 63):
+                np.testing.assert_array_equal(rec[k], o.gather(k, robot_ids), err_msg="gather step %d world %d" % (step, ids[k]))
+    assert _compare_sampled(b, o, ids, "after 270 steps") == len(ids)
+
+
+def test_config5_full_size_sampled_worlds(sim, orc):
+    """BASELINE configs[4] on one GPU: 1,048,576 6v6 worlds (1.0 GB of state and commands), two command periods; 64
+    sampled worlds (ids k * 16384) bit-identical to the oracle, and the batch statistics see every world."""
+    W, R = 1 << 20, 12
+    ids = list(range(0, W, 16384))
+    b = sim.WorldBatch(W, R)
+    o = orc.Worlds(len(ids), R, world_ids=ids)
+    T = os.cpu_count() or 1
+    for period in range(2):
+        b.gen_commands(period, 0); o.gen_commands(period, 0)
+        b.step(45); o.step(45, threads=T)
+    assert _compare_sampled(b, o, ids, "after 90 steps") == len(ids)
+    st = b.reduce_stats()
+    assert st["bad_worlds"] == 0 and st["contacts"] >= 13 * 2 * 30 * W   # every world settled on the ground for >= 30 steps
