@@ -167,6 +167,7 @@ typedef struct {
   float mu;   /* 0 disables the friction row */
   int spin;   /* ball-ground row in spin mode: friction row carries the angular term */
   float acc_n, acc_f, acc_p;
+  int sid;    /* static partner: 0 ceiling, 1..4 walls, 5..10 goal boxes, 11 ground; -1 for a pair row (warm-start study key) */
 } row_t;
 
 static float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -198,7 +199,7 @@ typedef struct {
 /* finish a row given (n, dist, a, b, e, mu): Bullet 2.82 setupContactConstraint */
 static void finish_row(const gen_ctx *g, row_t *r, float nx, float ny, float nz, float dist,
                        int a, int b, float e, float mu) {
-  r->nx = nx; r->ny = ny; r->nz = nz; r->a = a; r->b = b; r->mu = mu; r->spin = 0;
+  r->nx = nx; r->ny = ny; r->nz = nz; r->a = a; r->b = b; r->mu = mu; r->spin = 0; r->sid = -1;
   r->acc_n = r->acc_f = r->acc_p = 0.0f;
   float rvx = g->vel[a].x, rvy = g->vel[a].y, rvz = g->vel[a].z;
   if (b >= 0) { rvx = rvx - g->vel[b].x; rvy = rvy - g->vel[b].y; rvz = rvz - g->vel[b].z; }
@@ -243,6 +244,7 @@ static int gen_ground(const gen_ctx *g, int b, row_t *r) {
   float mu = MU;
   if (!ball && g->cflags && (g->cflags[b] & ORC_CMD_DRIVE)) mu = 0.0f; /* wheels replace sliding friction */
   finish_row(g, r, 0.0f, 0.0f, 1.0f, dist, b, -1, ball ? E_BALL_PLANE : E_ROBOT_PLANE, mu);
+  r->sid = 11;
   if (ball && g->spin_mode) {
     /* friction direction from the contact-point velocity (v + w x r_c), r_c = (0,0,-r) */
     float cvx = nmad(BALL_R, g->vel[b].w, g->vel[b].x); /* vel.w = omega_y */
@@ -269,22 +271,24 @@ static int gen_statics(const gen_ctx *g, const field_derived *d, int b, row_t *o
   float margin = ball ? g->ball_margin : MARGIN;
   float e = ball ? E_BALL_PLANE : E_ROBOT_PLANE;
   float dist;
+  int sid = 0; /* canonical index of the static solid being tested */
 #define EMIT(NX, NY, NZ, DIST, E)                                                     \
   do {                                                                                \
-    if (cnt < cap) finish_row(g, &out[cnt], (NX), (NY), (NZ), (DIST), b, -1, (E), MU); \
+    if (cnt < cap) { finish_row(g, &out[cnt], (NX), (NY), (NZ), (DIST), b, -1, (E), MU); out[cnt].sid = sid; } \
     cnt++;                                                                            \
   } while (0)
   dist = CEIL_Z - (pz + (ball ? BALL_R : ROBOT_ZHI));
   if (dist <= margin) EMIT(0.0f, 0.0f, -1.0f, dist, e);
-  dist = (px + d->limit_x) - rad;
+  dist = (px + d->limit_x) - rad; sid = 1;
   if (dist <= margin) EMIT(1.0f, 0.0f, 0.0f, dist, e);
-  dist = (d->limit_x - px) - rad;
+  dist = (d->limit_x - px) - rad; sid = 2;
   if (dist <= margin) EMIT(-1.0f, 0.0f, 0.0f, dist, e);
-  dist = (py + d->limit_y) - rad;
+  dist = (py + d->limit_y) - rad; sid = 3;
   if (dist <= margin) EMIT(0.0f, 1.0f, 0.0f, dist, e);
-  dist = (d->limit_y - py) - rad;
+  dist = (d->limit_y - py) - rad; sid = 4;
   if (dist <= margin) EMIT(0.0f, -1.0f, 0.0f, dist, e);
   for (int k = 0; k < 6; k++) {
+    sid = 5 + k;
     const float *lo = d->lo[k], *hi = d->hi[k];
     float nx, ny, nz;
     if (ball) {
@@ -403,9 +407,11 @@ int orc_sleep_substeps(float h) {
 }
 
 /* ---- one substep (Bullet internalSingleStepSimulation, STEP_SPEC 4) ------- */
+static int32_t warm_key(const row_t *r) { return (int32_t)(r->a | ((r->b + 1) << 8) | ((r->sid + 1) << 16)); }
+
 static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4 *pos,
                     orc_vec4 *vel, uint32_t *aux, const orc_cmd *cmd, float h, int ball_gravity,
-                    int sleep_substeps) {
+                    int sleep_substeps, orc_warm *warm) {
   const int N = R + 1, B = R;
   const float inv_h = 1.0f / h;
   const int spin_mode = (p->flags & ORC_F_BALL_SPIN) != 0;
@@ -569,6 +575,37 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   if (overflow) aux[ORC_AUX_STATUS] |= 1u << 16;
   aux[ORC_AUX_CONTACTS] += (uint32_t)(nrows + nground);
 
+  /* Warm starting -- STUDY ONLY (orc_step_warm; not part of STEP_SPEC v2, whose rows start from zero impulse:
+   * deviation D2).  Bullet 2.82 setupContactConstraint / setFrictionConstraintImpulse with SOLVER_USE_WARMSTARTING:
+   * a contact point that persisted starts at 0.85 x the impulses it ended the last substep with, applied to the
+   * solver velocities at set-up; here a point persists iff its key (bodies, static solid) had a row last substep. */
+  float wsx = pos[B].w, wsy = vel[B].w; /* ball spin as changed by a warm-started spin friction row */
+  if (warm) {
+    const float ball_im = 1.0f / BALL_M, sg = (2.5f * ball_im) / BALL_R;
+    for (int k = 0; k < nrows + N; k++) {
+      row_t *r;
+      if (k < nrows) r = &rows[k];
+      else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
+      const int32_t key = warm_key(r);
+      int hit = -1;
+      for (int c = 0; c < warm->n; c++) if (warm->key[c] == key) { hit = c; break; }
+      if (hit < 0) continue;
+      const int a = r->a, b = r->b;
+      const float ima = invm[a], imb = b >= 0 ? invm[b] : 0.0f;
+      r->acc_n = 0.85f * warm->acc_n[hit];
+      float ka = r->acc_n * ima;
+      vx[a] = mad(r->nx, ka, vx[a]); vy[a] = mad(r->ny, ka, vy[a]); vz[a] = mad(r->nz, ka, vz[a]);
+      if (b >= 0) { float kb = r->acc_n * imb; vx[b] = nmad(r->nx, kb, vx[b]); vy[b] = nmad(r->ny, kb, vy[b]); vz[b] = nmad(r->nz, kb, vz[b]); }
+      if (r->mu > 0.0f) {
+        r->acc_f = 0.85f * warm->acc_f[hit];
+        ka = r->acc_f * ima;
+        vx[a] = mad(r->tx, ka, vx[a]); vy[a] = mad(r->ty, ka, vy[a]); vz[a] = mad(r->tz, ka, vz[a]);
+        if (b >= 0) { float kb = r->acc_f * imb; vx[b] = nmad(r->tx, kb, vx[b]); vy[b] = nmad(r->ty, kb, vy[b]); vz[b] = nmad(r->tz, kb, vz[b]); }
+        if (r->spin) { float kw = r->acc_f * sg; wsx = mad(r->ty, kw, wsx); wsy = nmad(r->tx, kw, wsy); }
+      }
+    }
+  }
+
   /* 4.4 split-impulse pass (Bullet solveGroupCacheFriendlySplitImpulseIterations) */
   int deep = 0;
   for (int k = 0; k < nrows; k++) deep |= rows[k].push_target > 0.0f;
@@ -602,7 +639,7 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
 
   /* 4.5 velocity iterations: all normal rows, then all friction rows (Bullet
    * solveSingleIteration without SOLVER_INTERLEAVE_CONTACT_AND_FRICTION) */
-  float wx = pos[B].w, wy = vel[B].w; /* ball spin (omega_x, omega_y) */
+  float wx = wsx, wy = wsy; /* ball spin (omega_x, omega_y) */
   const float ball_invm = 1.0f / BALL_M;
   const float spin_meff = 1.0f / (ball_invm + 2.5f * ball_invm);
   const float spin_gain = (2.5f * ball_invm) / BALL_R; /* r / I */
@@ -663,6 +700,16 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
         wx = mad(r->ty, kw, wx);
         wy = nmad(r->tx, kw, wy);
       }
+    }
+  }
+
+  if (warm) { /* what the persisting contact points carry into the next substep */
+    warm->n = 0;
+    for (int k = 0; k < nrows + N; k++) {
+      const row_t *r;
+      if (k < nrows) r = &rows[k];
+      else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
+      if (warm->n < ORC_WARM_CAP) { warm->key[warm->n] = warm_key(r); warm->acc_n[warm->n] = r->acc_n; warm->acc_f[warm->n] = r->acc_f; warm->n++; }
     }
   }
 
@@ -749,6 +796,11 @@ static void step_events(const field_derived *d, int R, const orc_vec4 *pos, uint
 
 void orc_step(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *pos, orc_vec4 *vel,
               uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h) {
+  orc_step_warm(f, p, n_robots, pos, vel, aux, cmd, n_steps, substeps, h, 0);
+}
+
+void orc_step_warm(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *pos, orc_vec4 *vel,
+                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, orc_warm *warm) {
   field_derived d;
   derive_field(f, &d);
   const int sleep_substeps = orc_sleep_substeps(h);
@@ -757,7 +809,7 @@ void orc_step(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *p
     aux[ORC_AUX_STATUS] &= ~(1u << 15);
     /* Bullet stepSimulation: applyGravity() once, for the bodies that are active now (STEP_SPEC 3) */
     const int ball_gravity = ((aux[ORC_AUX_STATUS] >> ACT_SHIFT) & 3u) != ACT_ASLEEP;
-    for (int k = 0; k < substeps; k++) substep(&d, p, n_robots, pos, vel, aux, cmd, h, ball_gravity, sleep_substeps);
+    for (int k = 0; k < substeps; k++) substep(&d, p, n_robots, pos, vel, aux, cmd, h, ball_gravity, sleep_substeps, warm);
     step_events(&d, n_robots, pos, aux);
   }
 }

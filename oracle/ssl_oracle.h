@@ -92,6 +92,14 @@ void orc_step(const orc_field *f, const orc_params *p, int n_robots,
               orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux,
               const orc_cmd *cmd, int n_steps, int substeps, float h);
 
+/* STUDY ONLY (tools/warm_start_effect.py; deviation D2 of docs/STEP_SPEC.md): the same step with Bullet-style warm
+ * starting (0.85 x the impulses of the contact points that persisted from the previous substep).  `warm` is the
+ * per-world cache (zero-initialised = empty); NULL = orc_step.  Not part of the specification the CUDA kernel follows. */
+#define ORC_WARM_CAP 96
+typedef struct { int32_t n; int32_t key[ORC_WARM_CAP]; float acc_n[ORC_WARM_CAP], acc_f[ORC_WARM_CAP]; } orc_warm;
+void orc_step_warm(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *pos, orc_vec4 *vel,
+                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, orc_warm *warm);
+
 /* deterministic initial state: mode 0 = reference-style uniform
  * placement dropped from 0.5 m (reference src/sslsim.cpp:34-42, :446);
  * mode 1 = crowded +x penalty area, resting. */

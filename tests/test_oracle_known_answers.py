@@ -306,3 +306,40 @@ def test_declared_deviation_d4_contacts_use_the_chassis_radius_only(orc):
     wall = 9.0 / 2 + 0.25 + 0.45                                # FIELD_2015: field_length / 2 + boundary + referee = 5.2
     assert wall - 0.09 - 4e-3 < max_x < wall - 0.09 + 1e-3      # turned back at the chassis radius (within a substep's travel), not at the 0.10 wheel reach
     assert 0.18 - 3e-3 < min_gap < 0.18 + 8e-3                  # chassis to chassis (0.20 with both wheels in line)
+
+
+def test_warm_start_study_entry_point_leaves_the_spec_alone(orc):
+    """orc_step_warm (study of deviation D2, tools/warm_start_effect.py): with a NULL cache it is orc_step; with a cache a
+    single resting contact row gives the same result as the spec's cold start (the first update of an isolated row solves
+    it exactly either way), while a bounce off a wall does not (Bullet's warm-started friction impulse stays applied once
+    the normal impulse has been clamped to zero)."""
+    import ctypes as C
+    L = orc.lib()
+
+    class Warm(C.Structure):
+        _fields_ = [("n", C.c_int32), ("key", C.c_int32 * 96), ("acc_n", C.c_float * 96), ("acc_f", C.c_float * 96)]
+    L.orc_step_warm.argtypes = [C.POINTER(orc.Field), C.POINTER(orc.Params), C.c_int] + [C.c_void_p] * 4 + \
+        [C.c_int, C.c_int, C.c_float, C.POINTER(Warm)]
+
+    def run(warm, vy):
+        w = _one_world(orc, R=1)
+        w.pos[0, 0] = (0.0, 3.55, 0.025, 0.0); w.vel[0, 0] = (0.4, vy, 0.0, 0.0)   # resting on the ground, 0.06 m from the +y wall
+        w.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
+        cache = Warm()
+        for _ in range(40):
+            L.orc_step_warm(C.byref(w.field), C.byref(w.params), 1, orc._ptr(w.pos[0]), orc._ptr(w.vel[0]), orc._ptr(w.aux[0]),
+                            None, 1, 2, C.c_float(float(orc.H)), C.byref(cache) if warm else None)
+        return w.pos.copy(), w.vel.copy(), cache.n
+
+    ref = _one_world(orc, R=1)
+    ref.pos[0, 0] = (0.0, 3.55, 0.025, 0.0); ref.vel[0, 0] = (0.4, 0.0, 0.0, 0.0)
+    ref.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
+    ref.step(40)
+    p0, v0, _ = run(False, 0.0)
+    np.testing.assert_array_equal(p0, ref.pos); np.testing.assert_array_equal(v0, ref.vel)      # NULL cache = orc_step
+    p1, v1, n1 = run(True, 0.0)
+    assert n1 == 2                                                   # the two ground rows persist in the cache
+    np.testing.assert_allclose(p1, p0, atol=2e-6)                    # sliding on the ground only: same physics
+    pc, vc, _ = run(False, 1.5)
+    pw, vw, _ = run(True, 1.5)                                       # runs into the wall and bounces
+    assert np.abs(pw - pc).max() > 1e-4                              # the declared deviation D2 is visible here
