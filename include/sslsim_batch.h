@@ -48,7 +48,11 @@ struct SslSimParams {
   float mu_roll;
   float restitution_threshold; /* Bullet's m_restitutionVelocityThreshold: 0 = Bullet 2.82 (no threshold, the default
                                   here); 0.2 = btContactSolverInfo's default from Bullet 2.87 on */
-  float reserved[2];
+  float warmstart_factor;      /* Bullet's btContactSolverInfo::m_warmstartingFactor (SOLVER_USE_WARMSTARTING is in
+                                  Bullet's default solver mode): a contact row that had a row in the previous substep
+                                  starts at this factor x the impulses it ended with (docs/STEP_SPEC.md 4.5a).  Default
+                                  0.85 = Bullet; 0 = every row starts from zero (the cold-start step of spec v2) */
+  float reserved[1];
 };
 #define SSLSIM_F_BALL_SPIN 1u /* ball rolls (spin state + rolling resistance) instead of the reference's pure sliding */
 void sslsim_params_default(struct SslSimParams *p);
@@ -72,6 +76,22 @@ struct RobotCommand {
  * upstream); the ball takes (vx, vy, 0). */
 struct RobotReplacement { int32_t world; int32_t robot; float x, y, dir; };
 struct BallReplacement { int32_t world; float x, y, vx, vy; };
+
+/* The warm table: the fourth state array of a world beside pos / vel / aux (docs/STEP_SPEC.md 4.5a) -- the accumulated
+ * normal and friction impulse every contact row of the last substep ended with, keyed by what the row is between (Bullet
+ * keeps them in its persistent manifolds).  u32 words per world, N = n_robots + 1, cap = 32 for N <= 16, else 64:
+ *   [0, N)       sig[b]    byte k = 1 + id of the static solid in slot k of body b (0 = empty slot), k = 0..3; ids:
+ *                          0 ceiling, 1 wall -x, 2 wall +x, 3 wall -y, 4 wall +y, 5..10 the six goal boxes
+ *   [N, 5N)      sn[k][b]  normal impulse of that row (f32 bits);   [5N, 9N)  sf[k][b]  its friction impulse
+ *   [9N, 10N)    gn[b]     ground row of body b, normal impulse;    [10N, 11N) gf[b]    its friction impulse
+ *   [11N]        np        number of pair entries
+ *   [11N + 1 ..) pab[cap], pn[cap], pf[cap]   robot-robot (a = i < b = j) and ball-robot (a = ball, b = robot) rows:
+ *                          a | b << 8, normal impulse, friction impulse
+ * Slot and entry order carry no meaning; all zero = empty.  The step reads and rewrites it; snapshot / restore / fork
+ * carry it; every external write of a world's state (world_batch_write_state, replace_*, referee placement, the
+ * legacy setters, reset) clears that world's table -- the moved bodies' contact points are gone, and the other rows of
+ * that world start their next substep cold, as in spec v2.  world_batch_read_warm / write_warm move it explicitly. */
+#define SSLSIM_WARM_WORDS(n_robots) (11 * ((n_robots) + 1) + 1 + 3 * (((n_robots) + 1) <= 16 ? 32 : 64))
 
 /* aux words per world (8 x u32) */
 enum {
@@ -192,6 +212,11 @@ int world_batch_replace_balls(struct WorldBatch *batch, const struct BallReplace
 int world_batch_read_state(struct WorldBatch *batch, float *pos, float *vel, uint32_t *aux);
 int world_batch_write_state(struct WorldBatch *batch, const float *pos, const float *vel, const uint32_t *aux);
 int world_batch_read_aux(struct WorldBatch *batch, uint32_t *aux);
+/* the warm tables, [n_worlds][SSLSIM_WARM_WORDS(n_robots)] words (layout above).  write_state clears them, so a caller
+ * that moves a complete state between batches writes the state first and the tables second. */
+int world_batch_read_warm(struct WorldBatch *batch, uint32_t *warm);
+int world_batch_write_warm(struct WorldBatch *batch, const uint32_t *warm);
+int world_batch_warm_words(const struct WorldBatch *batch); /* words per world */
 /* selected worlds only: pos/vel [n][n_robots + 1][4] floats, aux [n][8] words (bulk form of the per-world getters) */
 int world_batch_read_worlds(struct WorldBatch *batch, const int *world_ids, int n, float *pos, float *vel, uint32_t *aux);
 /* zero-copy: device pointers of the live buffers (pos/vel: float4 [W][R+1];

@@ -86,6 +86,7 @@ void orc_params_default(orc_params *p) {
   p->dribble_reach = 0.03f;
   p->mu_roll = 0.03f;
   p->restitution_threshold = 0.0f; /* Bullet 2.82: none (0.2 is btContactSolverInfo's default from 2.87 on) */
+  p->warmstart_factor = 0.85f;     /* btContactSolverInfo::m_warmstartingFactor with SOLVER_USE_WARMSTARTING (Bullet default) */
 }
 
 /* ---- counter RNG --------------------------------------------------------- */
@@ -167,7 +168,7 @@ typedef struct {
   float mu;   /* 0 disables the friction row */
   int spin;   /* ball-ground row in spin mode: friction row carries the angular term */
   float acc_n, acc_f, acc_p;
-  int sid;    /* static partner: 0 ceiling, 1..4 walls, 5..10 goal boxes, 11 ground; -1 for a pair row (warm-start study key) */
+  int sid;    /* static partner: 0 ceiling, 1..4 walls, 5..10 goal boxes, 11 ground; -1 for a pair row (key of the warm table) */
 } row_t;
 
 static float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -407,11 +408,45 @@ int orc_sleep_substeps(float h) {
 }
 
 /* ---- one substep (Bullet internalSingleStepSimulation, STEP_SPEC 4) ------- */
-static int32_t warm_key(const row_t *r) { return (int32_t)(r->a | ((r->b + 1) << 8) | ((r->sid + 1) << 16)); }
+/* The warm table of one world (STEP_SPEC 4.5a), flat u32 words, the same layout in HBM (include/sslsim_batch.h):
+ *   [0, N)        sig[b]    byte k = 1 + sid of the static solid in slot k of body b (0 = slot empty), k = 0..3
+ *   [N, 5N)       sn[k][b]  accumulated normal impulse of that row at the end of the last substep (f32 bits)
+ *   [5N, 9N)      sf[k][b]  accumulated friction impulse
+ *   [9N, 10N)     gn[b]     ground row of body b: normal impulse (0 = none)
+ *   [10N, 11N)    gf[b]     ground row: friction impulse
+ *   [11N]         np        number of pair entries
+ *   [11N+1 ...)   pab[cap], pn[cap], pf[cap]   pair rows: a | b << 8, normal and friction impulse
+ * N = R + 1, cap = 32 for N <= 16, else 64.  Slot order within a body and entry order within the pair list carry no
+ * meaning (the oracle writes canonical order, the kernel arrival order); an all-zero table is the empty table. */
+int orc_warm_words(int n_robots) {
+  const int N = n_robots + 1, cap = N <= 16 ? 32 : MAX_SERIAL_ROWS;
+  return 11 * N + 1 + 3 * cap;
+}
+static float warm_f(const uint32_t *w) { float f; memcpy(&f, w, 4); return f; }
+static void warm_set(uint32_t *w, float f) { memcpy(w, &f, 4); }
+/* impulses the row's contact point ended the last substep with (0, 0 if it had no row) */
+static void warm_lookup(const uint32_t *warm, int N, int cap, const row_t *r, float *pn, float *pf) {
+  *pn = 0.0f; *pf = 0.0f;
+  if (r->b >= 0) {
+    const uint32_t *pt = warm + 11 * N;
+    const int np = (int)pt[0];
+    const uint32_t key = (uint32_t)(r->a | (r->b << 8));
+    for (int c = 0; c < np && c < cap; c++)
+      if (pt[1 + c] == key) { *pn = warm_f(&pt[1 + cap + c]); *pf = warm_f(&pt[1 + 2 * cap + c]); return; }
+  } else if (r->sid == 11) {
+    *pn = warm_f(&warm[9 * N + r->a]); *pf = warm_f(&warm[10 * N + r->a]);
+  } else {
+    const uint32_t sig = warm[r->a];
+    for (int k = 0; k < 4; k++)
+      if (((sig >> (8 * k)) & 0xffu) == (uint32_t)(r->sid + 1)) {
+        *pn = warm_f(&warm[N + k * N + r->a]); *pf = warm_f(&warm[5 * N + k * N + r->a]); return;
+      }
+  }
+}
 
 static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4 *pos,
                     orc_vec4 *vel, uint32_t *aux, const orc_cmd *cmd, float h, int ball_gravity,
-                    int sleep_substeps, orc_warm *warm) {
+                    int sleep_substeps, uint32_t *warm) {
   const int N = R + 1, B = R;
   const float inv_h = 1.0f / h;
   const int spin_mode = (p->flags & ORC_F_BALL_SPIN) != 0;
@@ -575,33 +610,37 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   if (overflow) aux[ORC_AUX_STATUS] |= 1u << 16;
   aux[ORC_AUX_CONTACTS] += (uint32_t)(nrows + nground);
 
-  /* Warm starting -- STUDY ONLY (orc_step_warm; not part of STEP_SPEC v2, whose rows start from zero impulse:
-   * deviation D2).  Bullet 2.82 setupContactConstraint / setFrictionConstraintImpulse with SOLVER_USE_WARMSTARTING:
-   * a contact point that persisted starts at 0.85 x the impulses it ended the last substep with, applied to the
-   * solver velocities at set-up; here a point persists iff its key (bodies, static solid) had a row last substep. */
+  /* 4.5a warm starting (Bullet 2.82 setupContactConstraint / setFrictionConstraintImpulse with SOLVER_USE_WARMSTARTING,
+   * btContactSolverInfo::m_warmstartingFactor = 0.85): a contact point that persisted from the last substep -- here: a
+   * row whose key (bodies, static solid) had a row then -- starts at factor x the impulses it ended that substep with,
+   * and the solver velocities receive those impulses at set-up, row by row in solver order, normal before friction
+   * (the friction impulse along the row's NEW direction, as Bullet does without friction-direction caching). */
   float wsx = pos[B].w, wsy = vel[B].w; /* ball spin as changed by a warm-started spin friction row */
-  if (warm) {
+  if (warm && p->warmstart_factor != 0.0f) {
+    const float wf = p->warmstart_factor;
     const float ball_im = 1.0f / BALL_M, sg = (2.5f * ball_im) / BALL_R;
     for (int k = 0; k < nrows + N; k++) {
       row_t *r;
       if (k < nrows) r = &rows[k];
       else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
-      const int32_t key = warm_key(r);
-      int hit = -1;
-      for (int c = 0; c < warm->n; c++) if (warm->key[c] == key) { hit = c; break; }
-      if (hit < 0) continue;
+      float pn, pf;
+      warm_lookup(warm, N, cap, r, &pn, &pf);
       const int a = r->a, b = r->b;
       const float ima = invm[a], imb = b >= 0 ? invm[b] : 0.0f;
-      r->acc_n = 0.85f * warm->acc_n[hit];
-      float ka = r->acc_n * ima;
-      vx[a] = mad(r->nx, ka, vx[a]); vy[a] = mad(r->ny, ka, vy[a]); vz[a] = mad(r->nz, ka, vz[a]);
-      if (b >= 0) { float kb = r->acc_n * imb; vx[b] = nmad(r->nx, kb, vx[b]); vy[b] = nmad(r->ny, kb, vy[b]); vz[b] = nmad(r->nz, kb, vz[b]); }
+      r->acc_n = wf * pn;
+      if (r->acc_n != 0.0f) {
+        float ka = r->acc_n * ima;
+        vx[a] = mad(r->nx, ka, vx[a]); vy[a] = mad(r->ny, ka, vy[a]); vz[a] = mad(r->nz, ka, vz[a]);
+        if (b >= 0) { float kb = r->acc_n * imb; vx[b] = nmad(r->nx, kb, vx[b]); vy[b] = nmad(r->ny, kb, vy[b]); vz[b] = nmad(r->nz, kb, vz[b]); }
+      }
       if (r->mu > 0.0f) {
-        r->acc_f = 0.85f * warm->acc_f[hit];
-        ka = r->acc_f * ima;
-        vx[a] = mad(r->tx, ka, vx[a]); vy[a] = mad(r->ty, ka, vy[a]); vz[a] = mad(r->tz, ka, vz[a]);
-        if (b >= 0) { float kb = r->acc_f * imb; vx[b] = nmad(r->tx, kb, vx[b]); vy[b] = nmad(r->ty, kb, vy[b]); vz[b] = nmad(r->tz, kb, vz[b]); }
-        if (r->spin) { float kw = r->acc_f * sg; wsx = mad(r->ty, kw, wsx); wsy = nmad(r->tx, kw, wsy); }
+        r->acc_f = wf * pf;
+        if (r->acc_f != 0.0f) {
+          float ka = r->acc_f * ima;
+          vx[a] = mad(r->tx, ka, vx[a]); vy[a] = mad(r->ty, ka, vy[a]); vz[a] = mad(r->tz, ka, vz[a]);
+          if (b >= 0) { float kb = r->acc_f * imb; vx[b] = nmad(r->tx, kb, vx[b]); vy[b] = nmad(r->ty, kb, vy[b]); vz[b] = nmad(r->tz, kb, vz[b]); }
+          if (r->spin) { float kw = r->acc_f * sg; wsx = mad(r->ty, kw, wsx); wsy = nmad(r->tx, kw, wsy); }
+        }
       }
     }
   }
@@ -703,14 +742,30 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
     }
   }
 
-  if (warm) { /* what the persisting contact points carry into the next substep */
-    warm->n = 0;
+  if (warm) { /* what the contact points carry into the next substep (Bullet solveGroupCacheFriendlyFinish) */
+    uint32_t *pt = warm + 11 * N;
+    int np = 0;
+    for (int b = 0; b < 11 * N; b++) warm[b] = 0;
     for (int k = 0; k < nrows + N; k++) {
       const row_t *r;
       if (k < nrows) r = &rows[k];
       else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
-      if (warm->n < ORC_WARM_CAP) { warm->key[warm->n] = warm_key(r); warm->acc_n[warm->n] = r->acc_n; warm->acc_f[warm->n] = r->acc_f; warm->n++; }
+      if (r->b >= 0) {
+        pt[1 + np] = (uint32_t)(r->a | (r->b << 8));
+        warm_set(&pt[1 + cap + np], r->acc_n); warm_set(&pt[1 + 2 * cap + np], r->acc_f);
+        np++;
+      } else if (r->sid == 11) {
+        warm_set(&warm[9 * N + r->a], r->acc_n); warm_set(&warm[10 * N + r->a], r->acc_f);
+      } else {
+        int slot = 0;
+        while (slot < 4 && ((warm[r->a] >> (8 * slot)) & 0xffu)) slot++;
+        if (slot < 4) {
+          warm[r->a] |= (uint32_t)(r->sid + 1) << (8 * slot);
+          warm_set(&warm[N + slot * N + r->a], r->acc_n); warm_set(&warm[5 * N + slot * N + r->a], r->acc_f);
+        }
+      }
     }
+    pt[0] = (uint32_t)np;
   }
 
   /* 4.6 touches, rolling resistance, peak speed */
@@ -800,7 +855,7 @@ void orc_step(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *p
 }
 
 void orc_step_warm(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *pos, orc_vec4 *vel,
-                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, orc_warm *warm) {
+                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, uint32_t *warm) {
   field_derived d;
   derive_field(f, &d);
   const int sleep_substeps = orc_sleep_substeps(h);
@@ -914,27 +969,30 @@ int orc_gather(int R, const orc_vec4 *pos, const int *ids, float *out) {
 /* ---- many worlds, optional threads (timing baseline) ------------------------ */
 typedef struct {
   const orc_field *f; const orc_params *p; int R, w0, w1;
-  orc_vec4 *pos, *vel; uint32_t *aux; const orc_cmd *cmd; int n_steps, substeps; float h;
+  orc_vec4 *pos, *vel; uint32_t *aux; const orc_cmd *cmd; int n_steps, substeps; float h; uint32_t *warm;
 } job_t;
 
 static void *job_run(void *arg) {
   job_t *j = (job_t *)arg;
   int N = j->R + 1;
+  const size_t ww = (size_t)orc_warm_words(j->R);
   for (int w = j->w0; w < j->w1; w++)
-    orc_step(j->f, j->p, j->R, j->pos + (size_t)w * N, j->vel + (size_t)w * N, j->aux + (size_t)w * 8,
-             j->cmd ? j->cmd + (size_t)w * j->R : 0, j->n_steps, j->substeps, j->h);
+    orc_step_warm(j->f, j->p, j->R, j->pos + (size_t)w * N, j->vel + (size_t)w * N, j->aux + (size_t)w * 8,
+                  j->cmd ? j->cmd + (size_t)w * j->R : 0, j->n_steps, j->substeps, j->h,
+                  j->warm ? j->warm + (size_t)w * ww : 0);
   return 0;
 }
 
 void orc_step_many(const orc_field *f, const orc_params *p, int R, int W, orc_vec4 *pos, orc_vec4 *vel,
-                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, int threads) {
+                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, int threads,
+                   uint32_t *warm) {
   if (threads < 1) threads = 1;
   if (threads > 256) threads = 256;
   job_t jobs[256];
   pthread_t th[256];
   for (int t = 0; t < threads; t++) {
     job_t j = {f, p, R, (int)((long long)W * t / threads), (int)((long long)W * (t + 1) / threads),
-               pos, vel, aux, cmd, n_steps, substeps, h};
+               pos, vel, aux, cmd, n_steps, substeps, h, warm};
     jobs[t] = j;
   }
   if (threads == 1) { job_run(&jobs[0]); return; }

@@ -50,7 +50,8 @@ typedef struct {
   float dribble_kd, dribble_cd, dribble_amax, dribble_reach;
   float mu_roll;
   float restitution_threshold; /* Bullet m_restitutionVelocityThreshold: 0 = Bullet 2.82 (none); 0.2 = Bullet >= 2.87 */
-  float reserved[2];
+  float warmstart_factor;      /* Bullet m_warmstartingFactor, default 0.85; 0 = no warm starting (spec v2) */
+  float reserved[1];
 } orc_params;
 
 /* per robot command, 32 bytes; schema: reference protos/grSim_Commands.proto:1-14 */
@@ -92,13 +93,14 @@ void orc_step(const orc_field *f, const orc_params *p, int n_robots,
               orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux,
               const orc_cmd *cmd, int n_steps, int substeps, float h);
 
-/* STUDY ONLY (tools/warm_start_effect.py; deviation D2 of docs/STEP_SPEC.md): the same step with Bullet-style warm
- * starting (0.85 x the impulses of the contact points that persisted from the previous substep).  `warm` is the
- * per-world cache (zero-initialised = empty); NULL = orc_step.  Not part of the specification the CUDA kernel follows. */
-#define ORC_WARM_CAP 96
-typedef struct { int32_t n; int32_t key[ORC_WARM_CAP]; float acc_n[ORC_WARM_CAP], acc_f[ORC_WARM_CAP]; } orc_warm;
+/* The same step with the world's warm table (STEP_SPEC 4.5a: Bullet's warm starting, every contact row that had a row
+ * with the same bodies / static solid in the previous substep starts at p->warmstart_factor x the impulses it ended
+ * that substep with).  `warm` is the world's table, orc_warm_words(n_robots) u32 words, layout documented in
+ * ssl_oracle.c and include/sslsim_batch.h (identical to the device's); all zero = empty; it is read and rewritten by
+ * every substep.  warm == NULL (orc_step) or warmstart_factor == 0: every row starts from zero impulse (spec v2). */
+int orc_warm_words(int n_robots);
 void orc_step_warm(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *pos, orc_vec4 *vel,
-                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, orc_warm *warm);
+                   uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, uint32_t *warm);
 
 /* deterministic initial state: mode 0 = reference-style uniform
  * placement dropped from 0.5 m (reference src/sslsim.cpp:34-42, :446);
@@ -139,7 +141,7 @@ void orc_sincos(float x, float *s, float *c);
 void orc_step_many(const orc_field *f, const orc_params *p, int n_robots,
                    int n_worlds, orc_vec4 *pos, orc_vec4 *vel, uint32_t *aux,
                    const orc_cmd *cmd, int n_steps, int substeps, float h,
-                   int threads);
+                   int threads, uint32_t *warm /* [W][orc_warm_words] or NULL = cold rows */);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,7 @@ class SimParams(C.Structure):
                 ("wheel_kp", C.c_float), ("wheel_fmax", C.c_float), ("robot_yaw_inertia", C.c_float),
                 ("dribble_kd", C.c_float), ("dribble_cd", C.c_float), ("dribble_amax", C.c_float),
                 ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("restitution_threshold", C.c_float),
-                ("reserved", C.c_float * 2)]
+                ("warmstart_factor", C.c_float), ("reserved", C.c_float * 1)]
 
 
 class Vec2(C.Structure):
@@ -124,6 +124,7 @@ BATCH_SYMBOLS = [
     ("world_batch_replace_robots", _I, [_VP, _VP, _I]), ("world_batch_replace_balls", _I, [_VP, _VP, _I]),
     ("world_batch_read_state", _I, [_VP, _VP, _VP, _VP]), ("world_batch_write_state", _I, [_VP, _VP, _VP, _VP]),
     ("world_batch_read_aux", _I, [_VP, _VP]),
+    ("world_batch_read_warm", _I, [_VP, _VP]), ("world_batch_write_warm", _I, [_VP, _VP]), ("world_batch_warm_words", _I, [_VP]),
     ("world_batch_device_state", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     ("world_batch_gather_detections", _I, [_VP, _VP, _I, _VP, C.c_size_t]),
     ("world_batch_detection_record_size", C.c_size_t, [_VP]),
@@ -388,6 +389,17 @@ class WorldBatch:
         vel = None if vel is None else np.ascontiguousarray(vel, np.float32)
         aux = None if aux is None else np.ascontiguousarray(aux, np.uint32)
         self._ck(lib().world_batch_write_state(self._h, _ptr(pos), _ptr(vel), _ptr(aux)))
+
+    def read_warm(self):
+        """the warm tables (docs/STEP_SPEC.md 4.5a; layout in include/sslsim_batch.h): [W, world_batch_warm_words] u32"""
+        warm = np.empty((self.W, lib().world_batch_warm_words(self._h)), np.uint32)
+        self._ck(lib().world_batch_read_warm(self._h, _ptr(warm)))
+        return warm
+
+    def write_warm(self, warm):
+        warm = np.ascontiguousarray(warm, np.uint32)
+        assert warm.shape == (self.W, lib().world_batch_warm_words(self._h))
+        self._ck(lib().world_batch_write_warm(self._h, _ptr(warm)))
 
     def gather_detections(self, world_ids):
         ids = np.ascontiguousarray(world_ids, np.int32)

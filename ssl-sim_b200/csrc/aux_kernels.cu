@@ -97,7 +97,16 @@ __global__ void gen_commands(RobotCommand *cmd, int W, int R, uint64_t seed, uin
 
 /* K2: sparse scatter, one thread per record; later records win (applied in order by one thread
  * per (world, body) is not needed: duplicates are resolved by taking the highest record index). */
-__global__ void replace_robots(float4 *pos, int W, int R, const RobotReplacement *recs, int n) {
+__device__ __forceinline__ void clear_warm(uint32_t *warm, int ww, int world) {
+  /* an external write of a world's state empties its warm table (include/sslsim_batch.h): the moved body's contact
+   * points are gone, the others start their next substep cold.  Zero sig / ground words and a zero pair count are the
+   * empty table; the impulse words behind them are dead */
+  if (!warm) return;
+  uint32_t *t = warm + (size_t)world * ww;
+  for (int k = 0; k < ww; ++k) t[k] = 0u;
+}
+
+__global__ void replace_robots(float4 *pos, uint32_t *warm, int ww, int W, int R, const RobotReplacement *recs, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const RobotReplacement rec = recs[t];
@@ -105,9 +114,11 @@ __global__ void replace_robots(float4 *pos, int W, int R, const RobotReplacement
   for (int u = t + 1; u < n; ++u) /* a later record for the same body supersedes this one */
     if (recs[u].world == rec.world && recs[u].robot == rec.robot) return;
   pos[(size_t)rec.world * (R + 1) + rec.robot] = make_float4(rec.x, rec.y, DROP_Z, rec.dir);
+  clear_warm(warm, ww, rec.world);
 }
 
-__global__ void replace_balls(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, const BallReplacement *recs, int n) {
+__global__ void replace_balls(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int ww, int W, int R,
+                              const BallReplacement *recs, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const BallReplacement rec = recs[t];
@@ -118,6 +129,7 @@ __global__ void replace_balls(float4 *pos, float4 *vel, uint32_t *aux, int W, in
   pos[i] = make_float4(rec.x, rec.y, DROP_Z, 0.0f);
   vel[i] = make_float4(rec.vx, rec.vy, 0.0f, 0.0f);
   aux[(size_t)rec.world * 8 + SSLSIM_AUX_STATUS] &= SSLSIM_STATUS_KEEP_ON_WAKE; /* reference :387 body.activate(true) */
+  clear_warm(warm, ww, rec.world);
 }
 
 /* K3: one warp per observed world; record = 6 floats ball + 7 floats per robot */
@@ -146,8 +158,8 @@ __global__ void gather_detections(const float4 *pos, int W, int R, const int *wo
 }
 
 /* referee restart placement (STEP_SPEC 7): one thread per world */
-__global__ void referee_restart(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, float field_length,
-                                float field_width) {
+__global__ void referee_restart(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int ww, int W, int R,
+                                float field_length, float field_width) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   uint32_t *a = aux + (size_t)w * 8;
@@ -166,10 +178,12 @@ __global__ void referee_restart(float4 *pos, float4 *vel, uint32_t *aux, int W, 
   vel[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   a[SSLSIM_AUX_STATUS] = st & ~(7u << 8) & SSLSIM_STATUS_KEEP_ON_WAKE; /* edge state cleared; the placed ball is awake */
   a[SSLSIM_AUX_RESTARTS] += 1u;
+  clear_warm(warm, ww, w);
 }
 
 /* fork: one warp per destination world copies the source world's bodies and aux words */
-__global__ void fork_worlds(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, int src, const int *dst, int n) {
+__global__ void fork_worlds(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int ww, int W, int R, int src,
+                            const int *dst, int n) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const int d = dst[warp];
@@ -180,6 +194,8 @@ __global__ void fork_worlds(float4 *pos, float4 *vel, uint32_t *aux, int W, int 
     vel[(size_t)d * N + b] = vel[(size_t)src * N + b];
   }
   if (lane < 8) aux[(size_t)d * 8 + lane] = aux[(size_t)src * 8 + lane];
+  if (warm)
+    for (int k = lane; k < ww; k += 32) warm[(size_t)d * ww + k] = warm[(size_t)src * ww + k];
 }
 
 /* K4: grid-stride block reduction of the aux words into 8 u64 (atomics on the final add) */
@@ -239,17 +255,17 @@ cudaError_t sslsim_launch_gen_commands(RobotCommand *cmd, int W, int R, uint64_t
   return cudaGetLastError();
 }
 
-cudaError_t sslsim_launch_replace_robots(float4 *pos, int W, int R, const RobotReplacement *recs, int n,
-                                         cudaStream_t s) {
+cudaError_t sslsim_launch_replace_robots(float4 *pos, uint32_t *warm, int ww, int W, int R, const RobotReplacement *recs,
+                                         int n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  replace_robots<<<(n + 127) / 128, 128, 0, s>>>(pos, W, R, recs, n);
+  replace_robots<<<(n + 127) / 128, 128, 0, s>>>(pos, warm, ww, W, R, recs, n);
   return cudaGetLastError();
 }
 
-cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, const BallReplacement *recs,
-                                        int n, cudaStream_t s) {
+cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int ww, int W, int R,
+                                        const BallReplacement *recs, int n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  replace_balls<<<(n + 127) / 128, 128, 0, s>>>(pos, vel, aux, W, R, recs, n);
+  replace_balls<<<(n + 127) / 128, 128, 0, s>>>(pos, vel, aux, warm, ww, W, R, recs, n);
   return cudaGetLastError();
 }
 
@@ -260,17 +276,17 @@ cudaError_t sslsim_launch_gather(const float4 *pos, int W, int R, const int *wor
   return cudaGetLastError();
 }
 
-cudaError_t sslsim_launch_referee(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, float field_length,
-                                  float field_width, cudaStream_t s) {
+cudaError_t sslsim_launch_referee(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int ww, int W, int R,
+                                  float field_length, float field_width, cudaStream_t s) {
   if (W <= 0) return cudaSuccess;
-  referee_restart<<<(W + 255) / 256, 256, 0, s>>>(pos, vel, aux, W, R, field_length, field_width);
+  referee_restart<<<(W + 255) / 256, 256, 0, s>>>(pos, vel, aux, warm, ww, W, R, field_length, field_width);
   return cudaGetLastError();
 }
 
-cudaError_t sslsim_launch_fork(float4 *pos, float4 *vel, uint32_t *aux, int W, int R, int src, const int *dst, int n,
-                               cudaStream_t s) {
+cudaError_t sslsim_launch_fork(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int ww, int W, int R, int src,
+                               const int *dst, int n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  fork_worlds<<<(n + 3) / 4, 128, 0, s>>>(pos, vel, aux, W, R, src, dst, n);
+  fork_worlds<<<(n + 3) / 4, 128, 0, s>>>(pos, vel, aux, warm, ww, W, R, src, dst, n);
   return cudaGetLastError();
 }
 

@@ -69,7 +69,7 @@ static void batch_free(WorldBatch *b) {
   if (b->ev_main) cudaEventDestroy(b->ev_main);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (World *w : b->views) delete w;
-  cudaFree(b->d_pos); cudaFree(b->d_vel); cudaFree(b->d_aux); cudaFree(b->d_cmd);
+  cudaFree(b->d_pos); cudaFree(b->d_vel); cudaFree(b->d_aux); cudaFree(b->d_warm); cudaFree(b->d_cmd);
   cudaFree(b->d_robot_ids); cudaFree(b->d_world_ids); cudaFree(b->d_gather); cudaFree(b->d_stats);
   cudaFree(b->d_rep); cudaFree(b->d_field); cudaFree(b->d_prof); cudaFree(b->d_seq);
   if (b->h_gather) cudaFreeHost(b->h_gather);
@@ -121,6 +121,10 @@ WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_
             sslsim_check(b, cudaMalloc(&b->d_pos, nb * sizeof(float4)), "cudaMalloc(pos)") &&
             sslsim_check(b, cudaMalloc(&b->d_vel, nb * sizeof(float4)), "cudaMalloc(vel)") &&
             sslsim_check(b, cudaMalloc(&b->d_aux, (size_t)n_worlds * 8 * sizeof(uint32_t)), "cudaMalloc(aux)") &&
+            sslsim_check(b, cudaMalloc(&b->d_warm, (size_t)n_worlds * SSLSIM_WARM_WORDS(b->cap_bodies - 1) * sizeof(uint32_t)),
+                         "cudaMalloc(warm)") &&
+            sslsim_check(b, cudaMemsetAsync(b->d_warm, 0, (size_t)n_worlds * SSLSIM_WARM_WORDS(b->cap_bodies - 1) * sizeof(uint32_t),
+                                            b->stream), "cudaMemset(warm)") &&
             sslsim_check(b, cudaMalloc(&b->d_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)") &&
             sslsim_check(b, cudaMalloc(&b->d_robot_ids, SSLSIM_MAX_BODIES * sizeof(int)), "cudaMalloc(ids)") &&
             sslsim_check(b, cudaMalloc(&b->d_field, sizeof(DevField)), "cudaMalloc(field)") &&
@@ -137,11 +141,17 @@ WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_
   return b;
 }
 
+cudaError_t sslsim_clear_warm(WorldBatch *b, int first, int count) {
+  const size_t ww = (size_t)sslsim_warm_words(b);
+  return cudaMemsetAsync(b->d_warm + (size_t)first * ww, 0, (size_t)count * ww * sizeof(uint32_t), b->stream);
+}
+
 static StepArgs step_args(const WorldBatch *b, int first, int count, const RobotCommand *cmd, int n_steps, int substeps,
                           float h, int steps_per_period, long long cmd_period_stride) {
   const size_t N = (size_t)b->R + 1;
   StepArgs a;
   a.pos = b->d_pos + first * N; a.vel = b->d_vel + first * N; a.aux = b->d_aux + (size_t)first * 8;
+  a.warm = b->d_warm + (size_t)first * sslsim_warm_words(b);
   a.cmd = cmd ? cmd + (size_t)first * b->R : nullptr;
   a.n_worlds = count; a.n_robots = b->R; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
   a.steps_per_period = steps_per_period; a.cmd_period_stride = cmd_period_stride;
@@ -198,6 +208,8 @@ void sslsim_params_default(struct SslSimParams *p) {
   p->dribble_amax = 12.0f;
   p->dribble_reach = 0.03f;
   p->mu_roll = 0.03f;
+  p->restitution_threshold = 0.0f;
+  p->warmstart_factor = 0.85f; /* Bullet: btContactSolverInfo::m_warmstartingFactor, SOLVER_USE_WARMSTARTING on by default */
 }
 
 struct WorldBatch *new_world_batch(const struct FieldGeometry *field, int n_worlds, int robots_per_team, int device,
@@ -218,6 +230,7 @@ int world_batch_reset(struct WorldBatch *b, uint64_t seed, int init_mode) {
   SSLSIM_RANGE("world_batch_reset");
   b->seed = seed;
   CK(sslsim_launch_init(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->field, seed, b->world0, init_mode, b->stream));
+  CK(sslsim_clear_warm(b, 0, b->W));
   b->frame = 0; b->timestamp = 0.0f;
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;
@@ -453,7 +466,7 @@ int world_batch_replace_robots(struct WorldBatch *b, const struct RobotReplaceme
   int rc = ensure_rep(b, (size_t)n * sizeof(RobotReplacement));
   if (rc) return rc;
   CK(cudaMemcpyAsync(b->d_rep, recs, (size_t)n * sizeof(RobotReplacement), cudaMemcpyHostToDevice, b->stream));
-  CK(sslsim_launch_replace_robots(b->d_pos, b->W, b->R, (const RobotReplacement *)b->d_rep, n, b->stream));
+  CK(sslsim_launch_replace_robots(b->d_pos, b->d_warm, sslsim_warm_words(b), b->W, b->R, (const RobotReplacement *)b->d_rep, n, b->stream));
   CK(cudaStreamSynchronize(b->stream)); /* the staging buffer is reused by the next call */
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;
@@ -467,7 +480,7 @@ int world_batch_replace_balls(struct WorldBatch *b, const struct BallReplacement
   int rc = ensure_rep(b, (size_t)n * sizeof(BallReplacement));
   if (rc) return rc;
   CK(cudaMemcpyAsync(b->d_rep, recs, (size_t)n * sizeof(BallReplacement), cudaMemcpyHostToDevice, b->stream));
-  CK(sslsim_launch_replace_balls(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, (const BallReplacement *)b->d_rep, n, b->stream));
+  CK(sslsim_launch_replace_balls(b->d_pos, b->d_vel, b->d_aux, b->d_warm, sslsim_warm_words(b), b->W, b->R, (const BallReplacement *)b->d_rep, n, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;
@@ -510,8 +523,29 @@ int world_batch_write_state(struct WorldBatch *b, const float *pos, const float 
   if (pos) CK(cudaMemcpyAsync(b->d_pos, pos, nb, cudaMemcpyHostToDevice, b->stream));
   if (vel) CK(cudaMemcpyAsync(b->d_vel, vel, nb, cudaMemcpyHostToDevice, b->stream));
   if (aux) CK(cudaMemcpyAsync(b->d_aux, aux, (size_t)b->W * 8 * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+  CK(sslsim_clear_warm(b, 0, b->W)); /* the written bodies' contact points are gone (include/sslsim_batch.h) */
   CK(cudaStreamSynchronize(b->stream));
   for (World *w : b->views) w->mirror_valid = false;
+  return SSLSIM_OK;
+}
+
+int world_batch_warm_words(const struct WorldBatch *b) { return b ? sslsim_warm_words(b) : 0; }
+
+int world_batch_read_warm(struct WorldBatch *b, uint32_t *warm) {
+  ENTER(b);
+  SSLSIM_RANGE("world_batch_read_warm");
+  if (!warm) return SSLSIM_E_ARG;
+  CK(cudaMemcpyAsync(warm, b->d_warm, (size_t)b->W * sslsim_warm_words(b) * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return SSLSIM_OK;
+}
+
+int world_batch_write_warm(struct WorldBatch *b, const uint32_t *warm) {
+  ENTER(b);
+  SSLSIM_RANGE("world_batch_write_warm");
+  if (!warm) return SSLSIM_E_ARG;
+  CK(cudaMemcpyAsync(b->d_warm, warm, (size_t)b->W * sslsim_warm_words(b) * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
   return SSLSIM_OK;
 }
 
@@ -557,7 +591,7 @@ int world_batch_gather_detections(struct WorldBatch *b, const int *world_ids, in
 int world_batch_referee(struct WorldBatch *b) {
   ENTER(b);
   SSLSIM_RANGE("world_batch_referee");
-  CK(sslsim_launch_referee(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, b->field.field_length, b->field.field_width, b->stream));
+  CK(sslsim_launch_referee(b->d_pos, b->d_vel, b->d_aux, b->d_warm, sslsim_warm_words(b), b->W, b->R, b->field.field_length, b->field.field_width, b->stream));
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;
 }
@@ -565,7 +599,7 @@ int world_batch_referee(struct WorldBatch *b) {
 struct WorldSnapshot {
   int device, W, R;
   float4 *pos, *vel;
-  uint32_t *aux;
+  uint32_t *aux, *warm;
   unsigned int frame;
   float timestamp;
 };
@@ -577,10 +611,13 @@ struct WorldSnapshot *world_batch_snapshot(struct WorldBatch *b) {
   WorldSnapshot *s = new (std::nothrow) WorldSnapshot();
   if (!s) return nullptr;
   s->device = b->device; s->W = b->W; s->R = b->R; s->frame = b->frame; s->timestamp = b->timestamp;
-  s->pos = s->vel = nullptr; s->aux = nullptr;
+  s->pos = s->vel = nullptr; s->aux = nullptr; s->warm = nullptr;
   const size_t nb = (size_t)b->W * (b->R + 1) * sizeof(float4), na = (size_t)b->W * 8 * sizeof(uint32_t);
+  const size_t nw = (size_t)b->W * sslsim_warm_words(b) * sizeof(uint32_t);
   const bool ok = sslsim_check(b, cudaMalloc(&s->pos, nb), "snapshot alloc") && sslsim_check(b, cudaMalloc(&s->vel, nb), "snapshot alloc") &&
                   sslsim_check(b, cudaMalloc(&s->aux, na), "snapshot alloc") &&
+                  sslsim_check(b, cudaMalloc(&s->warm, nw), "snapshot alloc") &&
+                  sslsim_check(b, cudaMemcpyAsync(s->warm, b->d_warm, nw, cudaMemcpyDeviceToDevice, b->stream), "snapshot copy") &&
                   sslsim_check(b, cudaMemcpyAsync(s->pos, b->d_pos, nb, cudaMemcpyDeviceToDevice, b->stream), "snapshot copy") &&
                   sslsim_check(b, cudaMemcpyAsync(s->vel, b->d_vel, nb, cudaMemcpyDeviceToDevice, b->stream), "snapshot copy") &&
                   sslsim_check(b, cudaMemcpyAsync(s->aux, b->d_aux, na, cudaMemcpyDeviceToDevice, b->stream), "snapshot copy") &&
@@ -597,6 +634,7 @@ int world_batch_restore(struct WorldBatch *b, const struct WorldSnapshot *s) {
   CK(cudaMemcpyAsync(b->d_pos, s->pos, nb, cudaMemcpyDeviceToDevice, b->stream));
   CK(cudaMemcpyAsync(b->d_vel, s->vel, nb, cudaMemcpyDeviceToDevice, b->stream));
   CK(cudaMemcpyAsync(b->d_aux, s->aux, na, cudaMemcpyDeviceToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_warm, s->warm, (size_t)b->W * sslsim_warm_words(b) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, b->stream));
   b->frame = s->frame; b->timestamp = s->timestamp;
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;
@@ -605,7 +643,7 @@ int world_batch_restore(struct WorldBatch *b, const struct WorldSnapshot *s) {
 void world_snapshot_free(struct WorldSnapshot *s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->pos); cudaFree(s->vel); cudaFree(s->aux);
+  cudaFree(s->pos); cudaFree(s->vel); cudaFree(s->aux); cudaFree(s->warm);
   delete s;
 }
 
@@ -617,7 +655,7 @@ int world_batch_fork(struct WorldBatch *b, int src, const int *dst, int n) {
   int rc = ensure_rep(b, (size_t)n * sizeof(int));
   if (rc) return rc;
   CK(cudaMemcpyAsync(b->d_rep, dst, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-  CK(sslsim_launch_fork(b->d_pos, b->d_vel, b->d_aux, b->W, b->R, src, (const int *)b->d_rep, n, b->stream));
+  CK(sslsim_launch_fork(b->d_pos, b->d_vel, b->d_aux, b->d_warm, sslsim_warm_words(b), b->W, b->R, src, (const int *)b->d_rep, n, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   for (World *w : b->views) w->mirror_valid = false;
   return SSLSIM_OK;

@@ -44,6 +44,7 @@ struct WorldBatch {
   SslSimParams params{};
   float4 *d_pos = nullptr, *d_vel = nullptr;
   uint32_t *d_aux = nullptr;
+  uint32_t *d_warm = nullptr;             /* warm tables [W][SSLSIM_WARM_WORDS(R)] (allocated for cap_bodies - 1 robots) */
   RobotCommand *d_cmd = nullptr;          /* owned command buffer (lazy) */
   const RobotCommand *cmd_active = nullptr; /* what the step kernel reads; NULL = passive robots */
   int *d_robot_ids = nullptr;
@@ -89,6 +90,9 @@ struct World {
 };
 
 bool sslsim_check(WorldBatch *b, cudaError_t e, const char *what);
+static inline int sslsim_warm_words(const WorldBatch *b) { return SSLSIM_WARM_WORDS(b->R); }
+/* empties the warm tables of worlds [first, first + count) on the batch stream (every external state write does) */
+cudaError_t sslsim_clear_warm(WorldBatch *b, int first, int count);
 int sslsim_join_chunks(WorldBatch *b); /* orders the batch stream after everything queued on the chunk streams */
 extern "C" int sslsim_ensure_cmd_buffer(WorldBatch *b); /* the batch-owned command buffer, zeroed (= passive robots) on first use */
 WorldBatch *sslsim_batch_create(const FieldGeometry *field, int n_worlds, int n_robots, int cap_bodies, int device,

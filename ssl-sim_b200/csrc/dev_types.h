@@ -23,6 +23,7 @@ struct StepArgs {
   float4 *pos;   /* [W][R+1] {x,y,z,yaw}; ball (last): {x,y,z,omega_x} */
   float4 *vel;   /* [W][R+1] {vx,vy,vz,yaw rate}; ball: {vx,vy,vz,omega_y} */
   uint32_t *aux; /* [W][8] */
+  uint32_t *warm; /* [W][SSLSIM_WARM_WORDS(R)]: the warm tables (STEP_SPEC 4.5a), or NULL = every row starts from zero */
   const RobotCommand *cmd; /* [W][R] or NULL */
   int n_worlds, n_robots, n_steps, substeps;
   int steps_per_period;         /* > 0: command sequence, a new [W][R] block every so many steps */
@@ -65,16 +66,18 @@ cudaError_t sslsim_launch_init(float4 *pos, float4 *vel, uint32_t *aux, int n_wo
                                const FieldGeometry &g, uint64_t seed, uint64_t world0, int mode, cudaStream_t s);
 cudaError_t sslsim_launch_gen_commands(RobotCommand *cmd, int n_worlds, int n_robots, uint64_t seed,
                                        uint64_t world0, uint64_t period, int kind, cudaStream_t s);
-cudaError_t sslsim_launch_replace_robots(float4 *pos, int n_worlds, int n_robots, const RobotReplacement *recs,
-                                         int n, cudaStream_t s);
-cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots,
-                                        const BallReplacement *recs, int n, cudaStream_t s);
+/* warm / warm_words: the batch's warm tables (include/sslsim_batch.h); kernels that write a world's state from outside
+ * the step clear that world's table, fork copies it */
+cudaError_t sslsim_launch_replace_robots(float4 *pos, uint32_t *warm, int warm_words, int n_worlds, int n_robots,
+                                         const RobotReplacement *recs, int n, cudaStream_t s);
+cudaError_t sslsim_launch_replace_balls(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int warm_words,
+                                        int n_worlds, int n_robots, const BallReplacement *recs, int n, cudaStream_t s);
 cudaError_t sslsim_launch_gather(const float4 *pos, int n_worlds, int n_robots, const int *world_ids, int n,
                                  const int *robot_ids, float *out, cudaStream_t s);
-cudaError_t sslsim_launch_referee(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots,
-                                  float field_length, float field_width, cudaStream_t s);
-cudaError_t sslsim_launch_fork(float4 *pos, float4 *vel, uint32_t *aux, int n_worlds, int n_robots, int src,
-                               const int *dst, int n, cudaStream_t s);
+cudaError_t sslsim_launch_referee(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int warm_words, int n_worlds,
+                                  int n_robots, float field_length, float field_width, cudaStream_t s);
+cudaError_t sslsim_launch_fork(float4 *pos, float4 *vel, uint32_t *aux, uint32_t *warm, int warm_words, int n_worlds,
+                               int n_robots, int src, const int *dst, int n, cudaStream_t s);
 cudaError_t sslsim_selftest_math_launch(unsigned long long n, unsigned long long seed, unsigned long long *d_bad,
                                         cudaStream_t s);
 cudaError_t sslsim_launch_reduce(const float4 *pos, const float4 *vel, const uint32_t *aux, int n_worlds,

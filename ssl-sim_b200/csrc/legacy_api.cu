@@ -69,6 +69,7 @@ bool push(World *w) {
   return sslsim_check(b, cudaMemcpyAsync(b->d_pos + off, w->pos, N * sizeof(float4), cudaMemcpyHostToDevice, b->stream), "push pos") &&
          sslsim_check(b, cudaMemcpyAsync(b->d_vel + off, w->vel, N * sizeof(float4), cudaMemcpyHostToDevice, b->stream), "push vel") &&
          sslsim_check(b, cudaMemcpyAsync(b->d_aux + (size_t)w->index * 8, w->aux, 8 * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream), "push aux") &&
+         sslsim_check(b, sslsim_clear_warm(b, w->index, 1), "push warm") && /* a setter moved a body: its contact points are gone */
          sslsim_check(b, cudaStreamSynchronize(b->stream), "push sync");
 }
 
@@ -127,6 +128,11 @@ struct World *clone_world(const struct World *world) {
       world_batch_set_commands(b, tmp);
   }
   if (!push(w)) { delete_world_batch(b); delete w; return nullptr; }
+  /* the copy continues exactly where the source is: its warm table comes along (push emptied the copy's) */
+  if (cudaMemcpy(b->d_warm, sb->d_warm + (size_t)src->index * sslsim_warm_words(sb),
+                 (size_t)sslsim_warm_words(sb) * sizeof(uint32_t), cudaMemcpyDeviceToDevice) != cudaSuccess) {
+    delete_world_batch(b); delete w; return nullptr;
+  }
   w->mirror_valid = true;
   return w;
 }

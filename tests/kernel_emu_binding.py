@@ -29,7 +29,7 @@ def lib():
         L = C.CDLL(os.path.join(EMU_DIR, "libstep_kernel_emu.so"))
         vp = C.c_void_p
         L.emu_step_worlds.argtypes = [C.POINTER(ob.Field), C.POINTER(ob.Params), C.c_int, C.c_int, vp, vp, vp, vp,
-                                      C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_longlong, C.c_int, vp]
+                                      C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_longlong, C.c_int, vp, vp]
         L.emu_step_worlds.restype = C.c_int
         _LIB = L
     return _LIB
@@ -44,5 +44,6 @@ class EmuWorlds(ob.Worlds):
         stride = self.W * self.R if cmd_seq is not None else 0
         rc = lib().emu_step_worlds(C.byref(self.field), C.byref(self.params), self.R, self.W, ob._ptr(self.pos),
                                    ob._ptr(self.vel), ob._ptr(self.aux), ob._ptr(cmd), n_steps, substeps,
-                                   C.c_float(float(h)), lanes, steps_per_period, stride, threads, ob._ptr(prof))
+                                   C.c_float(float(h)), lanes, steps_per_period, stride, threads, ob._ptr(prof),
+                                   ob._ptr(self.warm))
         assert rc == 0

@@ -35,7 +35,7 @@ class Params(C.Structure):
                 ("wheel_kp", C.c_float), ("wheel_fmax", C.c_float), ("robot_yaw_inertia", C.c_float),
                 ("dribble_kd", C.c_float), ("dribble_cd", C.c_float), ("dribble_amax", C.c_float),
                 ("dribble_reach", C.c_float), ("mu_roll", C.c_float), ("restitution_threshold", C.c_float),
-                ("reserved", C.c_float * 2)]
+                ("warmstart_factor", C.c_float), ("reserved", C.c_float * 1)]
 
 
 CMD_DTYPE = np.dtype([("wheel", np.float32, 4), ("kickspeedx", np.float32), ("kickspeedz", np.float32),
@@ -84,7 +84,9 @@ def lib():
         L.orc_u01.restype = C.c_float
         L.orc_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_step_many.argtypes = [C.POINTER(Field), C.POINTER(Params), C.c_int, C.c_int, fp, fp, fp, fp,
-                                    C.c_int, C.c_int, C.c_float, C.c_int]
+                                    C.c_int, C.c_int, C.c_float, C.c_int, fp]
+        L.orc_warm_words.argtypes = [C.c_int]
+        L.orc_warm_words.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -126,6 +128,8 @@ class Worlds:
         self.cmd = None
         self.seed, self.world0 = seed, world0
         L = lib()
+        # the warm table (STEP_SPEC 4.5a): part of the world state; an external write of a world's state clears its row
+        self.warm = np.zeros((n_worlds, L.orc_warm_words(n_robots)), np.uint32)
         for w in range(n_worlds):
             L.orc_init_world(C.byref(self.field), n_robots, seed, self.ids[w], mode,
                              _ptr(self.pos[w]), _ptr(self.vel[w]), _ptr(self.aux[w]))
@@ -140,15 +144,47 @@ class Worlds:
     def step(self, n_steps=1, substeps=2, h=H, threads=1):
         lib().orc_step_many(C.byref(self.field), C.byref(self.params), self.R, self.W, _ptr(self.pos),
                             _ptr(self.vel), _ptr(self.aux), _ptr(self.cmd), n_steps, substeps,
-                            C.c_float(float(h)), threads)
+                            C.c_float(float(h)), threads, _ptr(self.warm))
+
+    def clear_warm(self, worlds=None):
+        """what every external state write does on the device (write_state, replacements, referee placement, setters)"""
+        if worlds is None:
+            self.warm[...] = 0
+        else:
+            self.warm[worlds] = 0
 
     def referee(self):
         L = lib()
-        return sum(L.orc_referee(C.byref(self.field), self.R, _ptr(self.pos[w]), _ptr(self.vel[w]), _ptr(self.aux[w]))
-                   for w in range(self.W))
+        n = 0
+        for w in range(self.W):
+            if L.orc_referee(C.byref(self.field), self.R, _ptr(self.pos[w]), _ptr(self.vel[w]), _ptr(self.aux[w])):
+                self.warm[w] = 0
+                n += 1
+        return n
 
     def gather(self, w, ids):
         out = np.zeros(6 + 7 * self.R, np.float32)
         ids = np.asarray(ids, np.int32)
         n = lib().orc_gather(self.R, _ptr(self.pos[w]), _ptr(ids), _ptr(out))
         return out[:n]
+
+
+def warm_entries(row, n_robots):
+    """one world's warm table as {key: (normal impulse bits, friction impulse bits)}: the slot / entry order, which
+    carries no meaning, drops out; entries whose two impulses are zero are the same as no entry"""
+    N = n_robots + 1
+    cap = 32 if N <= 16 else 64
+    row = np.asarray(row, np.uint32)
+    out = {}
+    for b in range(N):
+        sig = int(row[b])
+        for k in range(4):
+            sid = (sig >> (8 * k)) & 0xff
+            if sid:
+                out[("static", b, sid - 1)] = (int(row[N + k * N + b]), int(row[5 * N + k * N + b]))
+        out[("ground", b)] = (int(row[9 * N + b]), int(row[10 * N + b]))
+    pt = row[11 * N:]
+    for c in range(int(pt[0])):
+        ab = int(pt[1 + c])
+        out[("pair", ab & 0xff, ab >> 8)] = (int(pt[1 + cap + c]), int(pt[1 + 2 * cap + c]))
+    return {k: v for k, v in out.items() if (v[0] & 0x7fffffff) or (v[1] & 0x7fffffff)}

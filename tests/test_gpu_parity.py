@@ -286,6 +286,7 @@ def test_replacements(sim, orc):
     o.pos[7, 0] = (-2.0, 0.3, 0.5, 3.0)
     o.pos[4, R] = (0.5, 0.5, 0.5, 0.0)
     o.vel[4, R] = (2.0, -1.0, 0.0, 0.0)
+    o.clear_warm([2, 7, 4])            # a replacement empties its world's warm table (include/sslsim_batch.h)
     b.step(90); o.step(90)
     _compare(b.read_state(), o, 90)
 
@@ -319,6 +320,7 @@ def test_legacy_single_world_api(sim, orc):
     o.pos[0, 3] = (1.0, 2.0, 0.5, 0.7)
     o.pos[0, 12, :3] = (-1.0, 0.5, 0.5)
     o.aux[0, 0] &= 0x3FFFF      # ball_set_vec wakes the ball (reference src/sslsim.cpp:387 activate(true))
+    o.clear_warm()              # the setters empty the world's warm table; clone_world carries the table along
     c = w.clone()
     for _ in range(60):
         w.step(); c.step()
@@ -438,7 +440,7 @@ def test_snapshot_restore_and_fork(sim, orc):
         np.testing.assert_array_equal(pos[d], pos[3]); np.testing.assert_array_equal(vel[d], vel[3]); np.testing.assert_array_equal(aux[d], aux[3])
     o.cmd = cmd
     for d in (5, 9, 10):
-        o.pos[d], o.vel[d], o.aux[d] = o.pos[3], o.vel[3], o.aux[3]
+        o.pos[d], o.vel[d], o.aux[d], o.warm[d] = o.pos[3], o.vel[3], o.aux[3], o.warm[3]
     o.step(60)
     _compare((pos, vel, aux), o, 60)
 
@@ -476,6 +478,60 @@ def test_randomized_crowded_stress(sim, orc, R, lanes):
         o.step(10)
         _compare(b.read_state(), o, 10, "R=%d period %d" % (R, period))
     assert ((o.aux[:, 0] >> 16) & 1).mean() < 0.9     # most worlds are not in overflow, i.e. really compared
+
+
+def _same_warm(orc, b, o, tag=""):
+    gw = b.read_warm()
+    assert gw.shape == o.warm.shape
+    for w in range(o.W):
+        if not (int(o.aux[w, 0]) >> 16) & 1:
+            assert orc.warm_entries(gw[w], o.R) == orc.warm_entries(o.warm[w], o.R), "warm table of world %d %s" % (w, tag)
+
+
+@pytest.mark.parametrize("R,mode,fld", [(12, 0, "FIELD_2015"), (22, 1, "FIELD_DIV_A"), (5, 0, "FIELD_2014_SINGLE")])
+def test_warm_tables(sim, orc, R, mode, fld):
+    """STEP_SPEC 4.5a: the fourth state array.  The device's warm tables hold the oracle's impulses under the oracle's
+    keys (both lane mappings, lean and general path); they survive launch boundaries, snapshots and an explicit
+    read / write; an external state write empties them; warmstart_factor = 0 is the cold-start step of spec v2."""
+    W = 24
+    f = getattr(orc, fld)
+    b = sim.WorldBatch(W, R, fld=fld, init_mode=mode)
+    o = orc.Worlds(W, R, fld=f, mode=mode)
+    assert sim.default_params().warmstart_factor == np.float32(0.85)
+    assert b.read_warm().shape[1] == 11 * (R + 1) + 1 + 3 * (32 if R + 1 <= 16 else 64) and not b.read_warm().any()
+    for period, n in enumerate((1, 1, 29, 30, 30, 7)):             # launch boundaries anywhere
+        o.gen_commands(period, 1); b.set_commands(o.cmd)
+        b.step(n); o.step(n)
+        _compare(b.read_state(), o, n, "R=%d period %d" % (R, period))
+        _same_warm(orc, b, o, "R=%d period %d" % (R, period))
+    assert b.read_warm().any()
+    # snapshot / restore carries the table; so does an explicit state + table transfer into a second batch
+    snap = b.snapshot()
+    state, warm = b.read_state(), b.read_warm()
+    b2 = sim.WorldBatch(W, R, fld=fld, init_mode=mode)
+    b2.write_state(*state); b2.write_warm(warm); b2.set_commands(o.cmd)
+    b.step(20); b2.step(20); o.step(20)
+    first = b.read_state()
+    _compare(first, o, 20, "continued")
+    _compare(b2.read_state(), o, 20, "second batch")
+    b.restore(snap); b.step(20)
+    for x, y in zip(first, b.read_state()):
+        np.testing.assert_array_equal(x, y)
+    b.free_snapshot(snap)
+    # write_state empties the tables: the next step starts every row cold, like an oracle whose tables were cleared
+    b.write_state(*first); o.clear_warm()
+    assert not b.read_warm().any()
+    b.step(15); o.step(15)
+    _compare(b.read_state(), o, 15, "after write_state")
+    _same_warm(orc, b, o, "after write_state")
+    # factor 0: the tables stay empty and the result is the cold-start oracle's
+    c = sim.WorldBatch(W, R, fld=fld, init_mode=mode, params=sim.default_params(warmstart_factor=0.0))
+    oc = orc.Worlds(W, R, fld=f, mode=mode, params=orc.default_params(warmstart_factor=0.0))
+    oc.gen_commands(0, 1); c.set_commands(oc.cmd)
+    c.step(60); oc.step(60)
+    _compare(c.read_state(), oc, 60, "cold")
+    assert not c.read_warm().any()
+    assert np.abs(oc.pos - o.pos).max() > 0                         # and it is a different trajectory
 
 
 def test_referee_restart_placement(sim, orc):
@@ -773,6 +829,7 @@ def test_legacy_accessors_on_batch_members(sim, orc):
     L.robot_set_pos(w2.robot(0), sim.Pos2(0.0, 2.0, 0.0)); L.robot_set_pos(w2.robot(1), sim.Pos2(0.19, 2.0, 0.0))
     assert L.robot_is_touching_robot(w2.robot(0), w2.robot(1)) == 1 and L.robot_is_touching_robot(w2.robot(0), w2.robot(5)) in (0, 1)
     o.pos[2, 0] = (0.0, 2.0, 0.5, 0.0); o.pos[2, 1] = (0.19, 2.0, 0.5, 0.0)
+    o.clear_warm([5, 2])        # the setters empty the warm tables of the worlds they touched
     b.step(45); o.step(45)
     _compare(b.read_state(), o, 45)
     assert w5.frame_number == 165 and np.float32(w5.ball_vec()[0]) == o.pos[5, R, 0]

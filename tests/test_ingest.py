@@ -108,6 +108,7 @@ def test_ingest_udp_to_device_commands_and_replacements(sim, orc, pb, tmp_path, 
     slot = int(rr[0]["robot"])
     assert slot == 2 * 4 + 1
     o.pos[40, slot] = (rr[0]["x"], rr[0]["y"], 0.5, rr[0]["dir"])
+    o.clear_warm([3, 40])                                    # a replacement empties its world's warm table
     before = b.read_worlds([3, 40])[0].copy()
     b.step(90); o.step(90)
     pos, vel, aux = b.read_state()

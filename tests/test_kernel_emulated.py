@@ -17,6 +17,9 @@ def _same(o, e, what=""):
     np.testing.assert_array_equal(o.pos, e.pos, err_msg="pos " + what)
     np.testing.assert_array_equal(o.vel, e.vel, err_msg="vel " + what)
     np.testing.assert_array_equal(o.aux, e.aux, err_msg="aux " + what)
+    for w in range(o.W):   # the warm tables (STEP_SPEC 4.5a) hold the same impulses under the same keys
+        if not (int(o.aux[w, 0]) >> 16) & 1:
+            assert ob.warm_entries(o.warm[w], o.R) == ob.warm_entries(e.warm[w], e.R), "warm table of world %d %s" % (w, what)
 
 
 def _pair(W, R, **kw):

@@ -308,38 +308,61 @@ def test_declared_deviation_d4_contacts_use_the_chassis_radius_only(orc):
     assert 0.18 - 3e-3 < min_gap < 0.18 + 8e-3                  # chassis to chassis (0.20 with both wheels in line)
 
 
-def test_warm_start_study_entry_point_leaves_the_spec_alone(orc):
-    """orc_step_warm (study of deviation D2, tools/warm_start_effect.py): with a NULL cache it is orc_step; with a cache a
-    single resting contact row gives the same result as the spec's cold start (the first update of an isolated row solves
-    it exactly either way), while a bounce off a wall does not (Bullet's warm-started friction impulse stays applied once
-    the normal impulse has been clamped to zero)."""
-    import ctypes as C
-    L = orc.lib()
-
-    class Warm(C.Structure):
-        _fields_ = [("n", C.c_int32), ("key", C.c_int32 * 96), ("acc_n", C.c_float * 96), ("acc_f", C.c_float * 96)]
-    L.orc_step_warm.argtypes = [C.POINTER(orc.Field), C.POINTER(orc.Params), C.c_int] + [C.c_void_p] * 4 + \
-        [C.c_int, C.c_int, C.c_float, C.POINTER(Warm)]
-
-    def run(warm, vy):
-        w = _one_world(orc, R=1)
+def test_warm_starting_known_answers(orc):
+    """STEP_SPEC 4.5a (Bullet's SOLVER_USE_WARMSTARTING, factor 0.85).  warmstart_factor = 0 is the cold-start step of spec
+    v2; a body resting on the ground carries the impulse m g h of its ground row in the warm table; a single resting row
+    gives the same motion either way (the first update of an isolated row solves it exactly from any start), while a
+    bounce off a wall does not (Bullet's artefact: the warm-started friction impulse stays applied once the normal
+    impulse has been clamped back to zero, because friction rows are skipped while their normal impulse is zero)."""
+    def run(factor, vy, steps=40):
+        w = _one_world(orc, R=1, params=orc.default_params(warmstart_factor=factor))
         w.pos[0, 0] = (0.0, 3.55, 0.025, 0.0); w.vel[0, 0] = (0.4, vy, 0.0, 0.0)   # resting on the ground, 0.06 m from the +y wall
         w.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
-        cache = Warm()
-        for _ in range(40):
-            L.orc_step_warm(C.byref(w.field), C.byref(w.params), 1, orc._ptr(w.pos[0]), orc._ptr(w.vel[0]), orc._ptr(w.aux[0]),
-                            None, 1, 2, C.c_float(float(orc.H)), C.byref(cache) if warm else None)
-        return w.pos.copy(), w.vel.copy(), cache.n
+        w.step(steps)
+        return w
 
-    ref = _one_world(orc, R=1)
-    ref.pos[0, 0] = (0.0, 3.55, 0.025, 0.0); ref.vel[0, 0] = (0.4, 0.0, 0.0, 0.0)
-    ref.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
-    ref.step(40)
-    p0, v0, _ = run(False, 0.0)
-    np.testing.assert_array_equal(p0, ref.pos); np.testing.assert_array_equal(v0, ref.vel)      # NULL cache = orc_step
-    p1, v1, n1 = run(True, 0.0)
-    assert n1 == 2                                                   # the two ground rows persist in the cache
-    np.testing.assert_allclose(p1, p0, atol=2e-6)                    # sliding on the ground only: same physics
-    pc, vc, _ = run(False, 1.5)
-    pw, vw, _ = run(True, 1.5)                                       # runs into the wall and bounces
-    assert np.abs(pw - pc).max() > 1e-4                              # the declared deviation D2 is visible here
+    assert orc.default_params().warmstart_factor == np.float32(0.85)
+    cold, warm = run(0.0, 0.0), run(0.85, 0.0)
+    np.testing.assert_allclose(warm.pos, cold.pos, atol=2e-6)        # sliding on the ground only: same physics
+    ent = orc.warm_entries(warm.warm[0], 1)
+    assert set(ent) == {("ground", 0), ("ground", 1)}                # the two ground rows persist in the table
+    gn = np.array([ent[("ground", 0)][0], ent[("ground", 1)][0]], np.uint32).view(np.float32)
+    np.testing.assert_allclose(gn, [2.0 * 9.80665 / 120, 0.046 * 9.80665 / 120], rtol=1e-5)   # m g h
+    gf = np.array([ent[("ground", 0)][1]], np.uint32).view(np.float32)
+    assert abs(gf[0]) <= 0.25 * gn[0] * (1 + 1e-6)                   # inside the friction cone
+    # factor 0 with a table is bit for bit the step without one
+    ref = _one_world(orc, R=1, params=orc.default_params(warmstart_factor=0.0))
+    ref.pos[...] = 0; ref.pos[0, 0] = (0.0, 3.55, 0.025, 0.0); ref.vel[0, 0] = (0.4, 1.5, 0.0, 0.0); ref.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
+    import ctypes as C
+    L = orc.lib()
+    L.orc_step.argtypes = [C.POINTER(orc.Field), C.POINTER(orc.Params), C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float]
+    for _ in range(40):
+        L.orc_step(C.byref(ref.field), C.byref(ref.params), 1, orc._ptr(ref.pos[0]), orc._ptr(ref.vel[0]), orc._ptr(ref.aux[0]),
+                   None, 1, 2, C.c_float(float(orc.H)))
+    pc = run(0.0, 1.5)
+    np.testing.assert_array_equal(pc.pos, ref.pos); np.testing.assert_array_equal(pc.vel, ref.vel)
+    pw = run(0.85, 1.5)                                              # runs into the wall and bounces
+    assert np.abs(pw.pos - pc.pos).max() > 1e-4                      # what deviation D2 of spec v2 amounted to
+    # while the robot leans on the wall its wall row is in the table under the wall's id (+y wall = static solid 4)
+    lean = _one_world(orc, R=1)
+    lean.pos[0, 0] = (0.0, 3.612, 0.025, 0.0); lean.vel[0, 0] = (0.0, 0.5, 0.0, 0.0)
+    lean.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
+    lean.step(1, substeps=1)
+    assert ("static", 0, 4) in orc.warm_entries(lean.warm[0], 1)
+    lean.clear_warm([0])
+    assert not orc.warm_entries(lean.warm[0], 1)
+
+
+def test_warm_start_converges_a_stack_faster(orc):
+    """what warm starting is for: a robot pushed against a wall by another robot (three coupled rows) is closer to the
+    solver's fixed point after the same 10 iterations when the rows start from last substep's impulses"""
+    def residual(factor):
+        w = _one_world(orc, R=2, params=orc.default_params(warmstart_factor=factor))
+        w.pos[0, 0] = (5.2 - 0.09, 0.0, 0.025, 0.0)                  # touching the +x wall (FIELD_2015: 5.2)
+        w.pos[0, 1] = (5.2 - 0.09 - 0.18, 0.0, 0.025, 0.0)           # touching robot 0
+        w.pos[0, 2] = (0.0, 2.0, 0.0215, 0.0)
+        w.cmd = np.zeros((1, 2), orc.CMD_DTYPE)
+        w.cmd[0, 1]["wheel"] = (2.0, 0.0, 0.0, 0.0); w.cmd[0, 1]["flags"] = orc.CMD_DRIVE   # drives forward (+x) into robot 0
+        w.step(60)
+        return float(np.abs(w.vel[0, :2, 0]).max())
+    assert residual(0.85) < residual(0.0)                            # the pushed pair is nearer to rest

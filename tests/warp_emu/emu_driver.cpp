@@ -8,12 +8,12 @@
 extern "C" int emu_step_worlds(const FieldGeometry *field, const SslSimParams *params, int n_robots, int n_worlds,
                                float *pos, float *vel, uint32_t *aux, const RobotCommand *cmd, int n_steps,
                                int substeps, float h, int lanes, int steps_per_period, long long cmd_period_stride,
-                               int os_threads, unsigned *prof) {
+                               int os_threads, unsigned *prof, uint32_t *warm) {
   static DevField dfield; /* f_dev points here ("global memory" of the out-of-line general path) */
   StepArgs a;
   memset(&a, 0, sizeof a);
   sslsim_derive_field(field, &dfield);
-  a.pos = reinterpret_cast<float4 *>(pos); a.vel = reinterpret_cast<float4 *>(vel); a.aux = aux; a.cmd = cmd;
+  a.pos = reinterpret_cast<float4 *>(pos); a.vel = reinterpret_cast<float4 *>(vel); a.aux = aux; a.cmd = cmd; a.warm = warm;
   a.n_worlds = n_worlds; a.n_robots = n_robots; a.n_steps = n_steps; a.substeps = substeps; a.h = h;
   a.steps_per_period = steps_per_period; a.cmd_period_stride = cmd_period_stride;
   a.p = *params;

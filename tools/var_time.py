@@ -5,8 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sim = importlib.import_module("ssl-sim_b200")
 import torch
 
+WARM = float(os.environ.get("SSLSIM_WARM", "0.85"))   # warmstart_factor; 0 = the cold-start kernels of spec v2
+
 def run(W, R=12, P=10, reps=4, settle_periods=40):
-    b = sim.WorldBatch(W, R)
+    b = sim.WorldBatch(W, R, params=sim.default_params(warmstart_factor=WARM))
     b.gen_commands(0, 0); b.step(120)
     for p in range(1, settle_periods):
         b.gen_commands(p, 0); b.step(30)
@@ -28,4 +30,4 @@ if __name__ == "__main__":
     for W in sizes:
         v, ck = run(W, reps=8 if W <= 16384 else 3)
         out.append("W=%d %.4e" % (W, v))
-    print(tag, " | ".join(out), "ck", ck, flush=True)
+    print(tag, "warm=%g" % WARM, " | ".join(out), "ck", ck, flush=True)
