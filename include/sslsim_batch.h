@@ -80,18 +80,22 @@ struct BallReplacement { int32_t world; float x, y, vx, vy; };
 /* The warm table: the fourth state array of a world beside pos / vel / aux (docs/STEP_SPEC.md 4.5a) -- the accumulated
  * normal and friction impulse every contact row of the last substep ended with, keyed by what the row is between (Bullet
  * keeps them in its persistent manifolds).  u32 words per world, N = n_robots + 1, cap = 32 for N <= 16, else 64:
- *   [0, N)       sig[b]    byte k = 1 + id of the static solid in slot k of body b (0 = empty slot), k = 0..3; ids:
- *                          0 ceiling, 1 wall -x, 2 wall +x, 3 wall -y, 4 wall +y, 5..10 the six goal boxes
- *   [N, 5N)      sn[k][b]  normal impulse of that row (f32 bits);   [5N, 9N)  sf[k][b]  its friction impulse
- *   [9N, 10N)    gn[b]     ground row of body b, normal impulse;    [10N, 11N) gf[b]    its friction impulse
- *   [11N]        np        number of pair entries
- *   [11N + 1 ..) pab[cap], pn[cap], pf[cap]   robot-robot (a = i < b = j) and ball-robot (a = ball, b = robot) rows:
- *                          a | b << 8, normal impulse, friction impulse
- * Slot and entry order carry no meaning; all zero = empty.  The step reads and rewrites it; snapshot / restore / fork
- * carry it; every external write of a world's state (world_batch_write_state, replace_*, referee placement, the
- * legacy setters, reset) clears that world's table -- the moved bodies' contact points are gone, and the other rows of
- * that world start their next substep cold, as in spec v2.  world_batch_read_warm / write_warm move it explicitly. */
-#define SSLSIM_WARM_WORDS(n_robots) (11 * ((n_robots) + 1) + 1 + 3 * (((n_robots) + 1) <= 16 ? 32 : 64))
+ *   [0, N)        sig[b]    byte k = 1 + id of the static solid in slot k of body b (0 = empty slot), k = 0..3; slots
+ *                           hold the ceiling (id 0) and the six goal boxes (ids 5..10)
+ *   [N, 5N)       on[k][b]  normal impulse of that row (f32 bits);   [5N, 9N)  of[k][b]  its friction impulse
+ *   [9N, 11N)     gn[b], gf[b]     ground row of body b: normal, friction impulse
+ *   [11N, 13N)    wxn[b], wxf[b]   its row against a field wall of the x axis (a body cannot leave one wall of an axis
+ *                                  and reach the other within a substep, so the axis is the key)
+ *   [13N, 15N)    wyn[b], wyf[b]   the same for the y axis
+ *   [15N]         np        number of pair entries
+ *   [15N + 1 ..)  pab[cap], pn[cap], pf[cap]   robot-robot (a = i < b = j) and ball-robot (a = ball, b = robot) rows:
+ *                           a | b << 8, normal impulse, friction impulse
+ * Slot and entry order carry no meaning; an entry with two zero impulses is no entry; all zero = empty.  The step reads
+ * and rewrites it; snapshot / restore / fork carry it; every external write of a world's state (world_batch_write_state,
+ * replace_*, referee placement, the legacy setters, reset) clears that world's table -- the moved bodies' contact
+ * points are gone, and the other rows of that world start their next substep cold, as in spec v2.
+ * world_batch_read_warm / write_warm move it explicitly. */
+#define SSLSIM_WARM_WORDS(n_robots) (15 * ((n_robots) + 1) + 1 + 3 * (((n_robots) + 1) <= 16 ? 32 : 64))
 
 /* aux words per world (8 x u32) */
 enum {

@@ -409,18 +409,22 @@ int orc_sleep_substeps(float h) {
 
 /* ---- one substep (Bullet internalSingleStepSimulation, STEP_SPEC 4) ------- */
 /* The warm table of one world (STEP_SPEC 4.5a), flat u32 words, the same layout in HBM (include/sslsim_batch.h):
- *   [0, N)        sig[b]    byte k = 1 + sid of the static solid in slot k of body b (0 = slot empty), k = 0..3
- *   [N, 5N)       sn[k][b]  accumulated normal impulse of that row at the end of the last substep (f32 bits)
- *   [5N, 9N)      sf[k][b]  accumulated friction impulse
- *   [9N, 10N)     gn[b]     ground row of body b: normal impulse (0 = none)
- *   [10N, 11N)    gf[b]     ground row: friction impulse
- *   [11N]         np        number of pair entries
- *   [11N+1 ...)   pab[cap], pn[cap], pf[cap]   pair rows: a | b << 8, normal and friction impulse
+ *   [0, N)        sig[b]    byte k = 1 + id of the static solid in slot k of body b (0 = slot empty), k = 0..3; only the
+ *                           ceiling (id 0) and the goal boxes (ids 5..10) live in slots
+ *   [N, 5N)       on[k][b]  accumulated normal impulse of that row at the end of the last substep (f32 bits)
+ *   [5N, 9N)      of[k][b]  accumulated friction impulse
+ *   [9N, 11N)     gn[b], gf[b]     ground row of body b (0 = none)
+ *   [11N, 13N)    wxn[b], wxf[b]   its row against a field wall of the x axis (solids 1, 2: a body cannot leave one
+ *                                  and reach the other within a substep, so the axis is the key)
+ *   [13N, 15N)    wyn[b], wyf[b]   the same for the y axis (solids 3, 4)
+ *   [15N]         np        number of pair entries
+ *   [15N+1 ...)   pab[cap], pn[cap], pf[cap]   pair rows: a | b << 8, normal and friction impulse
  * N = R + 1, cap = 32 for N <= 16, else 64.  Slot order within a body and entry order within the pair list carry no
- * meaning (the oracle writes canonical order, the kernel arrival order); an all-zero table is the empty table. */
+ * meaning (the oracle writes canonical order, the kernel arrival order); an entry whose two impulses are zero is the
+ * same as no entry; an all-zero table is the empty table. */
 int orc_warm_words(int n_robots) {
   const int N = n_robots + 1, cap = N <= 16 ? 32 : MAX_SERIAL_ROWS;
-  return 11 * N + 1 + 3 * cap;
+  return 15 * N + 1 + 3 * cap;
 }
 static float warm_f(const uint32_t *w) { float f; memcpy(&f, w, 4); return f; }
 static void warm_set(uint32_t *w, float f) { memcpy(w, &f, 4); }
@@ -428,13 +432,16 @@ static void warm_set(uint32_t *w, float f) { memcpy(w, &f, 4); }
 static void warm_lookup(const uint32_t *warm, int N, int cap, const row_t *r, float *pn, float *pf) {
   *pn = 0.0f; *pf = 0.0f;
   if (r->b >= 0) {
-    const uint32_t *pt = warm + 11 * N;
+    const uint32_t *pt = warm + 15 * N;
     const int np = (int)pt[0];
     const uint32_t key = (uint32_t)(r->a | (r->b << 8));
     for (int c = 0; c < np && c < cap; c++)
       if (pt[1 + c] == key) { *pn = warm_f(&pt[1 + cap + c]); *pf = warm_f(&pt[1 + 2 * cap + c]); return; }
   } else if (r->sid == 11) {
     *pn = warm_f(&warm[9 * N + r->a]); *pf = warm_f(&warm[10 * N + r->a]);
+  } else if (r->sid >= 1 && r->sid <= 4) {
+    const int o = r->sid <= 2 ? 11 : 13;
+    *pn = warm_f(&warm[o * N + r->a]); *pf = warm_f(&warm[(o + 1) * N + r->a]);
   } else {
     const uint32_t sig = warm[r->a];
     for (int k = 0; k < 4; k++)
@@ -743,9 +750,11 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   }
 
   if (warm) { /* what the contact points carry into the next substep (Bullet solveGroupCacheFriendlyFinish) */
-    uint32_t *pt = warm + 11 * N;
+    uint32_t *pt = warm + 15 * N;
     int np = 0;
-    for (int b = 0; b < 11 * N; b++) warm[b] = 0;
+    uint32_t wall_seen[ORC_MAX_BODIES];
+    for (int b = 0; b < 15 * N; b++) warm[b] = 0;
+    for (int b = 0; b < N; b++) wall_seen[b] = 0;
     for (int k = 0; k < nrows + N; k++) {
       const row_t *r;
       if (k < nrows) r = &rows[k];
@@ -756,6 +765,13 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
         np++;
       } else if (r->sid == 11) {
         warm_set(&warm[9 * N + r->a], r->acc_n); warm_set(&warm[10 * N + r->a], r->acc_f);
+      } else if (r->sid >= 1 && r->sid <= 4) {
+        const int o = r->sid <= 2 ? 11 : 13;
+        const uint32_t bit = r->sid <= 2 ? 1u : 2u;
+        if (!(wall_seen[r->a] & bit)) { /* both walls of an axis at once (a field narrower than a margin): the first */
+          wall_seen[r->a] |= bit;
+          warm_set(&warm[o * N + r->a], r->acc_n); warm_set(&warm[(o + 1) * N + r->a], r->acc_f);
+        }
       } else {
         int slot = 0;
         while (slot < 4 && ((warm[r->a] >> (8 * slot)) & 0xffu)) slot++;

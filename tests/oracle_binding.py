@@ -183,7 +183,9 @@ def warm_entries(row, n_robots):
             if sid:
                 out[("static", b, sid - 1)] = (int(row[N + k * N + b]), int(row[5 * N + k * N + b]))
         out[("ground", b)] = (int(row[9 * N + b]), int(row[10 * N + b]))
-    pt = row[11 * N:]
+        out[("wall x", b)] = (int(row[11 * N + b]), int(row[12 * N + b]))
+        out[("wall y", b)] = (int(row[13 * N + b]), int(row[14 * N + b]))
+    pt = row[15 * N:]
     for c in range(int(pt[0])):
         ab = int(pt[1 + c])
         out[("pair", ab & 0xff, ab >> 8)] = (int(pt[1 + cap + c]), int(pt[1 + 2 * cap + c]))

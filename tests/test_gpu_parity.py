@@ -498,7 +498,7 @@ def test_warm_tables(sim, orc, R, mode, fld):
     b = sim.WorldBatch(W, R, fld=fld, init_mode=mode)
     o = orc.Worlds(W, R, fld=f, mode=mode)
     assert sim.default_params().warmstart_factor == np.float32(0.85)
-    assert b.read_warm().shape[1] == 11 * (R + 1) + 1 + 3 * (32 if R + 1 <= 16 else 64) and not b.read_warm().any()
+    assert b.read_warm().shape[1] == 15 * (R + 1) + 1 + 3 * (32 if R + 1 <= 16 else 64) and not b.read_warm().any()
     for period, n in enumerate((1, 1, 29, 30, 30, 7)):             # launch boundaries anywhere
         o.gen_commands(period, 1); b.set_commands(o.cmd)
         b.step(n); o.step(n)

@@ -343,12 +343,12 @@ def test_warm_starting_known_answers(orc):
     np.testing.assert_array_equal(pc.pos, ref.pos); np.testing.assert_array_equal(pc.vel, ref.vel)
     pw = run(0.85, 1.5)                                              # runs into the wall and bounces
     assert np.abs(pw.pos - pc.pos).max() > 1e-4                      # what deviation D2 of spec v2 amounted to
-    # while the robot leans on the wall its wall row is in the table under the wall's id (+y wall = static solid 4)
+    # while the robot leans on the wall its wall row is in the table under the wall's axis
     lean = _one_world(orc, R=1)
     lean.pos[0, 0] = (0.0, 3.612, 0.025, 0.0); lean.vel[0, 0] = (0.0, 0.5, 0.0, 0.0)
     lean.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
     lean.step(1, substeps=1)
-    assert ("static", 0, 4) in orc.warm_entries(lean.warm[0], 1)
+    assert ("wall y", 0) in orc.warm_entries(lean.warm[0], 1)
     lean.clear_warm([0])
     assert not orc.warm_entries(lean.warm[0], 1)
 

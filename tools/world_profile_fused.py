@@ -7,7 +7,9 @@ import torch
 L = sim.lib()
 L.world_batch_profile_counters.argtypes = [C.c_void_p, C.c_void_p]
 W, R, P = 4096, 12, 10
-b = sim.WorldBatch(W, R)
+WARM = float(os.environ.get("SSLSIM_WARM", "0.85"))   # warmstart_factor; 0 = cold-start kernels
+b = sim.WorldBatch(W, R, params=sim.default_params(warmstart_factor=WARM))
+print("warmstart_factor", WARM)
 b.gen_commands(0, 0); b.step(120)
 for p in range(1, 120):
     b.gen_commands(p, 0); b.step(30)
