@@ -21,6 +21,8 @@ One bench *step* = 10 command periods x 30 world-steps = 300 world-steps of ever
   cpu_baseline  the CPU oracle (restated-Bullet port; Bullet itself is not buildable here) on the host cores for a
             bounded sample of the same workload (N = 1, rank 0 only).
   configs_1 / config_3 / config_4  sub-results at N = 1: BASELINE.json configs[1], [2], [3] at their stated sizes.
+  cold_start  sub-result at N = 1: the headline workload with warmstart_factor = 0 (the cold-start step of spec v2 that
+            rounds 1 and 2 measured); everything else runs the default parameters, i.e. Bullet's warm starting (spec v3).
 
 `--impl reference` times that CPU oracle alone (rank 0 only) on a bounded sample of the same workload.
 """
@@ -139,6 +141,7 @@ def config_dict(args, world_size):
             "total_worlds": args.total_worlds, "worlds_per_gpu": per, "robots_per_world": args.robots,
             "world_steps_per_step": WORLD_STEPS_PER_STEP, "command_periods_per_step": PERIODS_PER_STEP,
             "substeps_per_world_step": 2,
+            "step": "docs/STEP_SPEC.md v3, default parameters: Bullet's warm starting on (warmstart_factor 0.85)",
             "sharding": "contiguous world ranges, no per-step collective; NCCL all-gather of the episode statistics",
             "l2": "no flush needed: one launch streams %.0f MiB per GPU (state + %d command blocks) > 126 MB L2"
                   % (per * (2 * 16 * (args.robots + 1) + 32 + PERIODS_PER_STEP * 32 * args.robots) / 2 ** 20,

@@ -203,9 +203,41 @@ def config_4(sim, dev, device, seed, check_parity, n_steps=600):
             "gather_bytes_per_step": 64 * (6 + 7 * R) * 4, "parity": par}
 
 
+def cold_start(sim, dev, device, seed, check_parity, K=3, PPL=10, W=1 << 20):
+    """The headline workload (configs[4]: 1,048,576 6v6 worlds, wheel commands) with warmstart_factor = 0, i.e. the
+    cold-start step of spec v2 that rounds 1 and 2 measured: what Bullet's warm starting (spec v3, the default) costs."""
+    R = 12
+    b = sim.WorldBatch(W, R, device=device, seed=seed, params=sim.default_params(warmstart_factor=0.0))
+    cmd_bytes = W * R * 32
+    stage = torch.empty(PPL * cmd_bytes, dtype=torch.uint8, device=dev)
+    sched = [(0, 120)]
+    b.gen_commands(0, 0)
+    b.step(120)
+
+    def step(k):
+        for j in range(PPL):
+            b.gen_commands_into(stage.data_ptr() + j * cmd_bytes, 1 + k * PPL + j, 0)
+            sched.append((1 + k * PPL + j, PERIOD_STEPS))
+        b.step_sequence_device(stage.data_ptr(), PPL, PERIOD_STEPS)
+    step(0)                                   # warm-up
+    b.enable_kernel_timing(True)
+    b.kernel_time(reset=True)
+    for k in range(1, 1 + K):
+        step(k)
+    ms, n = b.kernel_time(reset=True)
+    par = None
+    if check_parity:
+        par, _ = _parity(sim, b, list(range(0, W, W // 16)), R, seed, sched, params_kw={"warmstart_factor": 0.0})
+    b.close()
+    return {"workload": "configs[4] with SslSimParams.warmstart_factor = 0 (every contact row starts from zero impulse: the "
+                        "step of spec v2, rounds 1-2): %d 6v6 worlds, %d launches of 10 command periods" % (W, K),
+            "value": W * PERIOD_STEPS * PPL * K / (ms * 1e-3), "unit": "world-steps/s", "kernel_ms_per_launch": ms / n,
+            "parity": par}
+
+
 def run_all(sim, dev, device, seed, check_parity=True):
     out = {}
-    for name, fn in (("configs_1", config_1), ("config_3", config_3), ("config_4", config_4)):
+    for name, fn in (("configs_1", config_1), ("config_3", config_3), ("config_4", config_4), ("cold_start", cold_start)):
         try:
             out[name] = fn(sim, dev, device, seed, check_parity)
         except Exception as e:   # a sub-result must not take the headline line down

@@ -1,12 +1,12 @@
-"""Measured effect of deviation D2 (docs/STEP_SPEC.md section 9): Bullet warm-starts every contact point that persisted
-from the previous substep at 0.85 x its last impulses; the spec starts every row from zero.
+"""What warm starting (docs/STEP_SPEC.md 4.5a, spec v3) changes against the cold-start step of spec v2: Bullet warm-starts
+every contact point that persisted from the previous substep at 0.85 x its last impulses;
+spec v2 started every row from zero (its deviation D2, closed in v3; warmstart_factor = 0 still gives that step).
 
-The CPU oracle (test infrastructure) has a study-only entry point, orc_step_warm, that adds exactly that to the
-spec's solver (a contact point persists iff the same bodies / static solid had a row in the previous substep).  This
-script follows the WARM-started trajectory and, at every world-step, also takes the same step COLD (the spec) from the
-same state, and reports how far the two results are apart after that one step -- the per-step deviation north_star's
-tolerance (1e-4 m, 1e-3 rad per step) is stated in.  (Comparing two free-running trajectories would only measure chaos:
-robot contacts amplify a last-bit difference to centimetres within seconds.)
+This script follows the WARM-started trajectory (the default parameters) on the CPU oracle and, at every world-step, also
+takes the same step COLD (warmstart_factor = 0) from the same state, and reports how far the two results are apart after
+that one step -- the per-step deviation north_star's tolerance (1e-4 m, 1e-3 rad per step) is stated in.  (Comparing two
+free-running trajectories would only measure chaos: robot contacts amplify a last-bit difference to centimetres within
+seconds.)  profiles/r2_warm_start_effect.txt is its output.
 
 usage: python tools/warm_start_effect.py [config2|config3] [worlds] [steps]
 """
@@ -23,16 +23,7 @@ import oracle_binding as ob  # noqa: E402
 CFG = sys.argv[1] if len(sys.argv) > 1 else "config2"
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 STEPS = int(sys.argv[3]) if len(sys.argv) > 3 else 900
-CAP = 96
-
-
-class Warm(C.Structure):
-    _fields_ = [("n", C.c_int32), ("key", C.c_int32 * CAP), ("acc_n", C.c_float * CAP), ("acc_f", C.c_float * CAP)]
-
-
 L = ob.lib()
-vp = C.c_void_p
-L.orc_step_warm.argtypes = [C.POINTER(ob.Field), C.POINTER(ob.Params), C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.POINTER(Warm)]
 
 if CFG == "config3":
     R, kind = 22, 1
@@ -40,8 +31,9 @@ if CFG == "config3":
 else:
     R, kind = 12, 0
     w = ob.Worlds(W, R)
-cold = ob.Worlds(1, R, fld=(ob.FIELD_DIV_A if CFG == "config3" else ob.FIELD_2015))
-caches = [Warm() for _ in range(W)]
+# the cold step = the same oracle with warmstart_factor 0 (the step of spec v2); `w` runs the default (spec v3, 0.85)
+cold = ob.Worlds(1, R, fld=(ob.FIELD_DIV_A if CFG == "config3" else ob.FIELD_2015), params=ob.default_params(warmstart_factor=0.0))
+one = ob.Worlds(1, R, fld=(ob.FIELD_DIV_A if CFG == "config3" else ob.FIELD_2015))
 dpos, dvel, dyaw, rows_per_substep, differing, total = [], [], [], [], 0, 0
 ev_diff = 0
 for step in range(STEPS):
@@ -53,8 +45,10 @@ for step in range(STEPS):
         cold.cmd = w.cmd[i:i + 1].copy()
         cold.step(1)
         c0 = int(w.aux[i, 7])
-        L.orc_step_warm(C.byref(w.field), C.byref(w.params), R, ob._ptr(w.pos[i]), ob._ptr(w.vel[i]), ob._ptr(w.aux[i]),
-                        ob._ptr(w.cmd[i]), 1, 2, C.c_float(float(ob.H)), C.byref(caches[i]))
+        one.pos[0] = w.pos[i]; one.vel[0] = w.vel[i]; one.aux[0] = w.aux[i]; one.warm[0] = w.warm[i]
+        one.cmd = w.cmd[i:i + 1].copy()
+        one.step(1)
+        w.pos[i] = one.pos[0]; w.vel[i] = one.vel[0]; w.aux[i] = one.aux[0]; w.warm[i] = one.warm[0]
         if step < 120 and CFG != "config3":
             continue          # the drop from 0.5 m
         rows_per_substep.append((int(w.aux[i, 7]) - c0) / 2.0)
