@@ -409,7 +409,7 @@ def main():
             for p in range(WU * PPS):
                 o.gen_commands(1 + p, 0)
                 o.step(PERIOD_STEPS, threads=threads)
-            warm = (o.pos.copy(), o.vel.copy(), o.aux.copy())
+            at_snap = (o.pos.copy(), o.vel.copy(), o.aux.copy(), o.warm.copy())   # the whole state, warm tables included
             for p in range(WU * PPS, (WU + K) * PPS):
                 o.gen_commands(1 + p, 0)
                 o.step(PERIOD_STEPS, threads=threads)
@@ -418,7 +418,7 @@ def main():
             same = [all(np.array_equal(a[i], g[i]) for a, g in zip((o.pos, o.vel, o.aux), dev_state)) for i in range(len(mine))]
             bad_dev = sum(1 for i, s in enumerate(same) if ok_rows[i] and not s)
             if e2e_state is not None:
-                o.pos[:], o.vel[:], o.aux[:] = warm
+                o.pos[:], o.vel[:], o.aux[:], o.warm[:] = at_snap
                 for p in range((WU + K) * PPS):
                     o.gen_commands(100000 + p % N_HOST, 0)
                     o.step(PERIOD_STEPS, threads=threads)

@@ -7,16 +7,25 @@ import torch
 
 WARM = float(os.environ.get("SSLSIM_WARM", "0.85"))   # warmstart_factor; 0 = the cold-start kernels of spec v2
 
+CFG = os.environ.get("SSLSIM_CFG", "")   # "3": 11v11 crowded Division-A worlds with kicks and dribbling (size / 2 worlds)
+
 def run(W, R=12, P=10, reps=4, settle_periods=40):
-    b = sim.WorldBatch(W, R, params=sim.default_params(warmstart_factor=WARM))
-    b.gen_commands(0, 0); b.step(120)
+    kind = 0
+    if CFG == "3":
+        R, kind, W = 22, 1, W // 2
+        b = sim.WorldBatch(W, R, fld="FIELD_DIV_A", init_mode=1, params=sim.default_params(warmstart_factor=WARM))
+        settle_periods = 4
+    else:
+        kind = 1 if CFG == "4" else 0
+        b = sim.WorldBatch(W, R, params=sim.default_params(warmstart_factor=WARM))
+    b.gen_commands(0, kind); b.step(120)
     for p in range(1, settle_periods):
-        b.gen_commands(p, 0); b.step(30)
+        b.gen_commands(p, kind); b.step(30)
     stage = torch.empty(P * W * R * 32, dtype=torch.uint8, device="cuda")
     tot = 0.0
     for r in range(reps + 1):
         for k in range(P):
-            b.gen_commands_into(stage.data_ptr() + k * W * R * 32, 1000 + r * P + k, 0)
+            b.gen_commands_into(stage.data_ptr() + k * W * R * 32, 1000 + r * P + k, kind)
         b.sync(); b.timer_start(); b.step_sequence_device(stage.data_ptr(), P, 30); ms = b.timer_stop()
         if r: tot += ms
     st = b.reduce_stats()
@@ -30,4 +39,4 @@ if __name__ == "__main__":
     for W in sizes:
         v, ck = run(W, reps=8 if W <= 16384 else 3)
         out.append("W=%d %.4e" % (W, v))
-    print(tag, "warm=%g" % WARM, " | ".join(out), "ck", ck, flush=True)
+    print(tag, "cfg=%s warm=%g" % (CFG or "2/5", WARM), " | ".join(out), "ck", ck, flush=True)

@@ -8,7 +8,9 @@ import torch
 L = sim.lib()
 L.world_batch_profile_counters.argtypes = [C.c_void_p, C.c_void_p]
 W, R, P = 16384, 22, 10
-b = sim.WorldBatch(W, R, fld="FIELD_DIV_A", init_mode=1)
+WARM = float(os.environ.get("SSLSIM_WARM", "0.85"))   # warmstart_factor; 0 = cold-start kernels
+b = sim.WorldBatch(W, R, fld="FIELD_DIV_A", init_mode=1, params=sim.default_params(warmstart_factor=WARM))
+print("warmstart_factor", WARM)
 for p in range(4):
     b.gen_commands(p, 1); b.step(30)
 stage = torch.empty(P * W * R * 32, dtype=torch.uint8, device="cuda")
