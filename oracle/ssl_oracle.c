@@ -168,6 +168,7 @@ typedef struct {
   float mu;   /* 0 disables the friction row */
   int spin;   /* ball-ground row in spin mode: friction row carries the angular term */
   float acc_n, acc_f, acc_p;
+  float dist, l2; /* separation and squared lateral relative velocity at set-up (4.5a: does the contact point persist?) */
   int sid;    /* static partner: 0 ceiling, 1..4 walls, 5..10 goal boxes, 11 ground; -1 for a pair row (key of the warm table) */
 } row_t;
 
@@ -200,7 +201,7 @@ typedef struct {
 /* finish a row given (n, dist, a, b, e, mu): Bullet 2.82 setupContactConstraint */
 static void finish_row(const gen_ctx *g, row_t *r, float nx, float ny, float nz, float dist,
                        int a, int b, float e, float mu) {
-  r->nx = nx; r->ny = ny; r->nz = nz; r->a = a; r->b = b; r->mu = mu; r->spin = 0; r->sid = -1;
+  r->nx = nx; r->ny = ny; r->nz = nz; r->a = a; r->b = b; r->mu = mu; r->spin = 0; r->sid = -1; r->dist = dist;
   r->acc_n = r->acc_f = r->acc_p = 0.0f;
   float rvx = g->vel[a].x, rvy = g->vel[a].y, rvz = g->vel[a].z;
   if (b >= 0) { rvx = rvx - g->vel[b].x; rvy = rvy - g->vel[b].y; rvz = rvz - g->vel[b].z; }
@@ -225,6 +226,7 @@ static void finish_row(const gen_ctx *g, row_t *r, float nx, float ny, float nz,
   /* single friction direction along the lateral relative velocity */
   float lx = nmad(nx, vn, rvx), ly = nmad(ny, vn, rvy), lz = nmad(nz, vn, rvz);
   float l2 = dot3(lx, ly, lz, lx, ly, lz);
+  r->l2 = l2;
   if (l2 > FLT_EPS && l2 < L2_MAX) {
     float k = 1.0f / sqrtf(l2);
     r->tx = lx * k; r->ty = ly * k; r->tz = lz * k;
@@ -251,6 +253,7 @@ static int gen_ground(const gen_ctx *g, int b, row_t *r) {
     float cvx = nmad(BALL_R, g->vel[b].w, g->vel[b].x); /* vel.w = omega_y */
     float cvy = mad(BALL_R, g->pos[b].w, g->vel[b].y);  /* pos.w = omega_x */
     float l2 = dot2(cvx, cvy, cvx, cvy);
+    r->l2 = l2; /* the contact point of a rolling ball does not slide */
     if (l2 > FLT_EPS && l2 < L2_MAX) {
       float k = 1.0f / sqrtf(l2);
       r->tx = cvx * k; r->ty = cvy * k; r->tz = 0.0f;
@@ -626,12 +629,18 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
   if (warm && p->warmstart_factor != 0.0f) {
     const float wf = p->warmstart_factor;
     const float ball_im = 1.0f / BALL_M, sg = (2.5f * ball_im) / BALL_R;
+    /* Bullet's refreshContactPoints drops a manifold point whose two anchors have come apart by more than the contact
+     * breaking threshold (0.02) along the normal or across it; the narrowphase then adds a new point, which starts
+     * cold.  Here: the row is beyond the threshold now (only the ball's speed-dependent margin reaches further), or
+     * the two bodies slid by more than the threshold during the last substep (h x lateral relative velocity). */
+    const float vbreak = MARGIN * inv_h, l2_break = vbreak * vbreak;
     for (int k = 0; k < nrows + N; k++) {
       row_t *r;
       if (k < nrows) r = &rows[k];
       else { if (!has_ground[k - nrows]) continue; r = &ground[k - nrows]; }
       float pn, pf;
       warm_lookup(warm, N, cap, r, &pn, &pf);
+      if (!(r->dist <= MARGIN && r->l2 <= l2_break)) { pn = 0.0f; pf = 0.0f; } /* the point did not persist */
       const int a = r->a, b = r->b;
       const float ima = invm[a], imb = b >= 0 ? invm[b] : 0.0f;
       r->acc_n = wf * pn;

@@ -33,6 +33,7 @@ struct StepArgs {
    * are read as constant-bank operands instead of occupying registers for the whole launch */
   float inv_h, gh, h_over_m, h_over_inertia, ez;
   int sleep_substeps;    /* slow substeps after which the ball wants to sleep (Bullet: > 2 s) */
+  float warm_l2max;      /* (contact breaking threshold / h)^2: a contact point whose bodies slid faster did not persist (4.5a) */
   DevField f;            /* by value: constant bank */
   const DevField *f_dev; /* the same in global memory, for the out-of-line general path */
   SslSimParams p;

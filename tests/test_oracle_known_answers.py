@@ -353,6 +353,33 @@ def test_warm_starting_known_answers(orc):
     assert not orc.warm_entries(lean.warm[0], 1)
 
 
+def test_warm_start_needs_a_persisting_contact_point(orc):
+    """STEP_SPEC 4.5a, Bullet's refreshContactPoints: a point whose anchors came apart by more than the breaking threshold
+    (0.02 m along the normal, or across it within one substep = 2.4 m/s of lateral relative velocity) does not persist, so
+    its row starts cold.  A ball bouncing off the ground at speed is 4 cm up one substep later: without the rule the
+    bounce's friction impulse would be re-applied there and throw the ball backwards."""
+    def bounce(factor):
+        w = _one_world(orc, R=0, params=orc.default_params(warmstart_factor=factor))
+        w.pos[0, 0] = (0.0, 0.0, 0.10, 0.0); w.vel[0, 0] = (-2.4, -0.5, -5.8, 0.0)
+        w.step(6)
+        return w
+    cold, warm = bounce(0.0), bounce(0.85)
+    assert cold.vel[0, 0, 2] > 2.0                                    # it bounced
+    np.testing.assert_array_equal(warm.pos, cold.pos)                 # and nothing was warm-started on the way
+    np.testing.assert_array_equal(warm.vel, cold.vel)
+    # a robot sliding into the +y wall: along the wall slower than 2.4 m/s its points persist and the bounce differs
+    # from the cold one (see test_warm_starting_known_answers); faster than that they do not, and nothing differs
+    def wall(vx, factor):
+        w = _one_world(orc, R=1, params=orc.default_params(warmstart_factor=factor))
+        w.pos[0, 0] = (0.0, 3.55, 0.025, 0.0); w.vel[0, 0] = (vx, 1.5, 0.0, 0.0)
+        w.pos[0, 1] = (2.0, 0.0, 0.0215, 0.0)
+        w.step(4)                                                     # (the fast one is still above 2.4 m/s after 4 steps)
+        return w
+    assert np.abs(wall(0.4, 0.85).pos - wall(0.4, 0.0).pos).max() > 1e-4
+    np.testing.assert_array_equal(wall(3.0, 0.85).pos[0, 0], wall(3.0, 0.0).pos[0, 0])
+    np.testing.assert_array_equal(wall(3.0, 0.85).vel[0, 0], wall(3.0, 0.0).vel[0, 0])
+
+
 def test_warm_start_converges_a_stack_faster(orc):
     """what warm starting is for: a robot pushed against a wall by another robot (three coupled rows) is closer to the
     solver's fixed point after the same 10 iterations when the rows start from last substep's impulses"""
