@@ -758,7 +758,7 @@ static void substep(const field_derived *d, const orc_params *p, int R, orc_vec4
     }
   }
 
-  if (warm) { /* what the contact points carry into the next substep (Bullet solveGroupCacheFriendlyFinish) */
+  if (warm && p->warmstart_factor != 0.0f) { /* what the contact points carry into the next substep (Bullet solveGroupCacheFriendlyFinish); with warm starting off the table is left alone */
     uint32_t *pt = warm + 15 * N;
     int np = 0;
     uint32_t wall_seen[ORC_MAX_BODIES];

@@ -97,7 +97,8 @@ void orc_step(const orc_field *f, const orc_params *p, int n_robots,
  * with the same bodies / static solid in the previous substep starts at p->warmstart_factor x the impulses it ended
  * that substep with).  `warm` is the world's table, orc_warm_words(n_robots) u32 words, layout documented in
  * ssl_oracle.c and include/sslsim_batch.h (identical to the device's); all zero = empty; it is read and rewritten by
- * every substep.  warm == NULL (orc_step) or warmstart_factor == 0: every row starts from zero impulse (spec v2). */
+ * every substep.  warm == NULL (orc_step) or warmstart_factor == 0: every row starts from zero impulse (spec v2) and the
+ * table is neither read nor written. */
 int orc_warm_words(int n_robots);
 void orc_step_warm(const orc_field *f, const orc_params *p, int n_robots, orc_vec4 *pos, orc_vec4 *vel,
                    uint32_t *aux, const orc_cmd *cmd, int n_steps, int substeps, float h, uint32_t *warm);

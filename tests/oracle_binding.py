@@ -189,4 +189,5 @@ def warm_entries(row, n_robots):
     for c in range(int(pt[0])):
         ab = int(pt[1 + c])
         out[("pair", ab & 0xff, ab >> 8)] = (int(pt[1 + cap + c]), int(pt[1 + 2 * cap + c]))
-    return {k: v for k, v in out.items() if (v[0] & 0x7fffffff) or (v[1] & 0x7fffffff)}
+    z = lambda u: 0 if (u & 0x7fffffff) == 0 else u          # the sign of a zero is not part of the contract (STEP_SPEC 4.8)
+    return {k: (z(v[0]), z(v[1])) for k, v in out.items() if (v[0] & 0x7fffffff) or (v[1] & 0x7fffffff)}

@@ -604,6 +604,7 @@ def test_random_fields_tunables_and_commands(sim, orc, seed):
               wheel_kp=f32(1.0, 60.0), wheel_fmax=f32(0.5, 10.0), robot_yaw_inertia=f32(0.002, 0.05),
               dribble_kd=f32(0.0, 120.0), dribble_cd=f32(0.0, 20.0), dribble_amax=f32(0.0, 30.0),
               dribble_reach=f32(0.0, 0.06), mu_roll=f32(0.0, 0.2))
+    kw["warmstart_factor"] = [0.85, 0.85, 0.0, 0.5, 1.0][seed % 5]   # (a key of its own: the draws above stay as they were)
     b = sim.WorldBatch(W, R, fld=sim.FieldGeometry(*fld), params=sim.default_params(**kw), seed=77 + seed)
     o = orc.Worlds(W, R, fld=fld, params=orc.default_params(**kw), seed=77 + seed)
     if R + 1 <= 16 and rng.integers(0, 2):

@@ -138,7 +138,8 @@ def test_emulated_kernel_random_fields_tunables_and_commands(seed):
               wheel_kp=f32(1.0, 60.0), wheel_fmax=f32(0.5, 10.0), robot_yaw_inertia=f32(0.002, 0.05),
               dribble_kd=f32(0.0, 120.0), dribble_cd=f32(0.0, 20.0), dribble_amax=f32(0.0, 30.0),
               dribble_reach=f32(0.0, 0.06), mu_roll=f32(0.0, 0.2),
-              restitution_threshold=float(rng.choice([0.0, 0.2])))
+              restitution_threshold=float(rng.choice([0.0, 0.2])),
+              warmstart_factor=float(rng.choice([0.85, 0.85, 0.0, 0.5, 1.0])))
     o = ob.Worlds(W, R, fld=fld, params=ob.default_params(**kw), seed=77 + seed)
     e = ke.EmuWorlds(W, R, fld=fld, params=ob.default_params(**kw), seed=77 + seed)
     lanes = 32 if (R + 1 <= 16 and rng.integers(0, 2)) else 0
@@ -173,4 +174,6 @@ def test_emulated_kernel_random_fields_tunables_and_commands(seed):
         np.testing.assert_array_equal(o.aux[:, 0] >> 16, e.aux[:, 0] >> 16, err_msg=what)
         np.testing.assert_array_equal(o.pos[keep], e.pos[keep], err_msg="pos " + what)
         np.testing.assert_array_equal(o.vel[keep], e.vel[keep], err_msg="vel " + what)
+        for w in np.nonzero(keep)[0]:
+            assert ob.warm_entries(o.warm[w], R) == ob.warm_entries(e.warm[w], R), "warm table of world %d, %s" % (w, what)
         np.testing.assert_array_equal(o.aux[keep], e.aux[keep], err_msg="aux " + what)
