@@ -239,6 +239,10 @@ size_t world_batch_detection_record_size(const struct WorldBatch *batch);
 /* ---- legacy view: member i of the batch as a `struct World *` usable with
  * every sslsim.h call (host-mirrored; getters synchronise).  Owned by the batch. */
 struct World *world_batch_get_world(struct WorldBatch *batch, int index);
+/* the reverse: the batch a `struct World` lives in (a batch of one for new_world / clone_world results) and, if
+ * index is not NULL, its index there -- for what the reference's per-world getters do not expose (a robot's height,
+ * the aux words, the warm table: world_batch_read_worlds / read_warm on the result).  Borrowed, never NULL for a live world. */
+struct WorldBatch *world_get_batch(struct World *world, int *index);
 
 /* ---- referee restart placement (README goal 4, no upstream implementation).  For every world
  * whose last step raised a goal event the ball is put on the centre spot; after ball-out it is put back 0.1 m

@@ -128,7 +128,7 @@ BATCH_SYMBOLS = [
     ("world_batch_device_state", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     ("world_batch_gather_detections", _I, [_VP, _VP, _I, _VP, C.c_size_t]),
     ("world_batch_detection_record_size", C.c_size_t, [_VP]),
-    ("world_batch_get_world", _VP, [_VP, _I]),
+    ("world_batch_get_world", _VP, [_VP, _I]), ("world_get_batch", _VP, [_VP, C.POINTER(_I)]),
     ("world_batch_reduce_stats", _I, [_VP, C.POINTER(BatchStats)]),
     ("world_batch_snapshot", _VP, [_VP]), ("world_batch_restore", _I, [_VP, _VP]), ("world_snapshot_free", None, [_VP]),
     ("world_batch_fork", _I, [_VP, _I, _VP, _I]), ("world_batch_referee", _I, [_VP]),
@@ -650,6 +650,22 @@ class World:
         w = World(handle=h)
         w._owned = True
         return w
+
+    def full_state(self):
+        """(pos [N, 4], vel [N, 4], aux [8], warm [words]) of this world through world_get_batch: what the reference's
+        per-world getters do not expose (a robot's height and vertical velocity, the aux words, the warm table)"""
+        L = lib()
+        idx = _I(0)
+        bh = L.world_get_batch(self._h, C.byref(idx))
+        W, R = L.world_batch_world_count(bh), L.world_batch_robot_count(bh)
+        ids = np.array([idx.value], np.int32)
+        pos = np.empty((1, R + 1, 4), np.float32); vel = np.empty_like(pos); aux = np.empty((1, 8), np.uint32)
+        if L.world_batch_read_worlds(bh, _ptr(ids), 1, _ptr(pos), _ptr(vel), _ptr(aux)):
+            raise SslSimError("world_batch_read_worlds failed")
+        warm = np.empty((W, L.world_batch_warm_words(bh)), np.uint32)
+        if L.world_batch_read_warm(bh, _ptr(warm)):
+            raise SslSimError("world_batch_read_warm failed")
+        return pos[0], vel[0], aux[0], warm[idx.value]
 
     def step(self):
         lib().world_step(self._h)

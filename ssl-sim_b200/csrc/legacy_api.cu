@@ -230,6 +230,12 @@ void world_add_robot(struct World *world, int id, enum Team team) {
   push(world);
 }
 
+struct WorldBatch *world_get_batch(struct World *world, int *index) {
+  if (!world) return nullptr;
+  if (index) *index = world->index;
+  return B(world);
+}
+
 unsigned int world_get_frame_number(const struct World *world) { return B(world)->frame; }
 double world_get_timestamp(const struct World *world) { return (double)B(world)->timestamp; }
 struct btDiscreteDynamicsWorld *world_bt_dynamics(struct World *world) { (void)world; return nullptr; }

@@ -328,6 +328,26 @@ def test_legacy_single_world_api(sim, orc):
     for ww in (w, c):
         assert tuple(np.float32(v) for v in ww.ball_vec()) == tuple(o.pos[0, 12, :3])
         assert np.float32(ww.robot_pos(3)[0]) == o.pos[0, 3, 0]
+    # a clone taken in mid-run carries the warm table along: original and copy keep following the oracle bit for bit.
+    # (Robot 0 is dropped onto robot 1 first: the coupled pair / ground rows of a stack are where a lost table shows --
+    # continuing this state without its table moves the velocities in the sixth digit.)
+    x1, y1, _ = w.robot_pos(1)
+    L.robot_set_pos(w.robot(0), sim.Pos2(x1, y1, 0.0))
+    o.pos[0, 0] = (o.pos[0, 1, 0], o.pos[0, 1, 1], 0.5, 0.0); o.clear_warm()
+    for _ in range(40):
+        w.step()
+    o.step(40)
+    assert ("pair", 0, 1) in orc.warm_entries(o.warm[0], 12)                   # robot 0 rests on robot 1 now
+    c2 = w.clone()
+    for _ in range(45):
+        w.step(); c2.step()
+    o.step(45)
+    for ww in (w, c2):
+        pos, vel, aux, warm = ww.full_state()        # world_get_batch: heights and the warm table too
+        np.testing.assert_array_equal(pos, o.pos[0]); np.testing.assert_array_equal(vel, o.vel[0])
+        np.testing.assert_array_equal(aux, o.aux[0])
+        assert orc.warm_entries(warm, 12) == orc.warm_entries(o.warm[0], 12)
+    c2.close()
     assert L.world_bt_dynamics(w._h) is None and L.ball_bt_rigid_body(w.ball()) is None
     assert L.ball_get_speed2(w.ball()) == pytest.approx(float((o.vel[0, 12, :3] ** 2).sum()), rel=1e-6)
     c.close(); w.close()
